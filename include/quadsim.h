@@ -1,0 +1,170 @@
+/* quadsim.h -- C ABI of libquadsim.so: the B200 (sm_100a) quadrotor racing simulator.
+ *
+ * This is the drop-in boundary that sits UNDER the reference's Python `Quadcopter3DGates(VecEnv)` class
+ * (`3D quad race.ipynb:287-620` end-to-end Bebop model; `3D quad race INDI inner loop.ipynb:142-410` INDI variant).
+ * The reference has no FFI of its own (it is NumPy in notebook cells); the entry points below are the calls its
+ * env methods decompose into, and `INTEGRATION.md` shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *   - plain C, no exceptions: every call returns QS_OK (0) or a negative qs_status; qs_last_error() explains.
+ *   - "dev" pointers are CUDA device pointers on the handle's device, "host" pointers are ordinary host memory.
+ *   - the caller owns every buffer it passes; the handle owns the simulator state.
+ *   - all kernels are enqueued on the handle's stream (qs_set_stream); calls taking host pointers synchronise
+ *     that stream before returning, calls taking only device pointers are asynchronous.
+ *   - a handle is not thread-safe.  One process per GPU; a shard of a larger job sets qs_set_env_offset so that
+ *     the device RNG is keyed by the GLOBAL env index and results do not depend on the number of GPUs.
+ *
+ * State lives on the device as a struct-of-arrays of float4 planes (see DESIGN.md "Data layout"); the
+ * reference's array-of-structs views (`world_states (N,16|13)`, `disturbances (N,6)`, `target_gates`,
+ * `step_counts`) are produced on demand by qs_get_state / consumed by qs_set_state.
+ */
+#ifndef QUADSIM_H
+#define QUADSIM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qs_env qs_env; /* opaque */
+
+typedef enum {
+    QS_OK = 0,
+    QS_ERR_ARG = -1,    /* bad argument (NULL, out of range, misaligned) */
+    QS_ERR_CUDA = -2,   /* a CUDA runtime call failed; text in qs_last_error */
+    QS_ERR_STATE = -3,  /* call not valid for this handle (e.g. disturbances on an INDI env) */
+    QS_ERR_NOMEM = -4
+} qs_status;
+
+/* which model: f_func of `3D quad race.ipynb:65-152` (+ residual MLPs `:244-262`) or of the INDI notebook `:48-110` */
+typedef enum { QS_E2E = 0, QS_INDI = 1 } qs_variant;
+
+/* the three branches of step_wait (`3D quad race.ipynb:568-585`) */
+typedef enum {
+    QS_MODE_NORMAL = 0,             /* world_states = new_states; reset_(dones)                         `:581-585` */
+    QS_MODE_PAUSE_IF_COLLISION = 1, /* advance only envs that are not done, never reset                 `:573-580` */
+    QS_MODE_PAUSE = 2               /* env.pause: nothing advances, dones reported False, obs untouched `:570-572` */
+} qs_mode;
+
+/* who provides the reset draws of reset_ (`:452-493`) in QS_MODE_NORMAL */
+typedef enum {
+    QS_RESET_DEVICE = 0, /* fused in the step kernel: Philox4x32-10 keyed by (seed, global env, episode) -- fast path */
+    QS_RESET_HOST = 1    /* step leaves done envs un-reset; the host draws (np.random, reference order) and calls
+                            qs_apply_reset -- bit-for-bit the reference's reset values */
+} qs_reset_source;
+
+/* bits of the optional per-env flag byte written by qs_step */
+enum {
+    QS_F_DONE = 1,           /* max_steps | ground | gate_collision | out_of_bounds   `:566` */
+    QS_F_TRUNCATED = 2,      /* step_counts >= max_steps                              `:553` */
+    QS_F_GATE_PASSED = 4,    /*                                                       `:533` */
+    QS_F_GATE_COLLISION = 8, /*                                                       `:534` */
+    QS_F_GROUND = 16,        /* z_new > 0                                             `:543` */
+    QS_F_OUT_OF_BOUNDS = 32  /* |x|,|y| > 10 or |p|,|q|,|r| > 1000                    `:549` */
+};
+
+/* running totals accumulated on the device by qs_step when enabled with qs_enable_stats */
+typedef struct {
+    double reward_sum;
+    uint64_t env_steps;
+    uint64_t dones;
+    uint64_t truncated;
+    uint64_t gates_passed;
+    uint64_t gate_collisions;
+    uint64_t ground_collisions;
+    uint64_t out_of_bounds;
+} qs_stats;
+
+#define QS_MAX_GATES 255
+#define QS_THRUST_WEIGHTS 289 /* Linear(7,32): W[32][7], b[32]; Linear(32,1): W[1][32], b[1]  (row-major [out][in]) */
+#define QS_MOMENT_WEIGHTS 451 /* Linear(10,32): W[32][10], b[32]; Linear(32,3): W[3][32], b[3]                     */
+
+/* ---- sizes ------------------------------------------------------------------------------------------------ */
+int qs_state_len(int variant);                /* 16 (E2E) or 13 (INDI): width of world_states                     */
+int qs_obs_len(int variant, int gates_ahead); /* 20+4*ga (`:330`) or 13+4*ga (INDI `:185`): width of states       */
+const char *qs_version(void);
+
+/* ---- life cycle: Quadcopter3DGates.__init__ (`3D quad race.ipynb:288-360`) ------------------------------- */
+/* gate_pos (n_gates,3) / gate_yaw (n_gates) / start_pos (3) are host float32 (the reference casts with
+ * .astype(np.float32), `:298-300`).  The relative-gate tables of `:309-319` and cos/sin(gate_yaw) are computed
+ * here in float32; qs_set_track_tables can override them with the caller's own (NumPy's) values.
+ * stream: a cudaStream_t (NULL = default stream).  E2E handles start with the packaged residual weights unset:
+ * call qs_set_residual_weights before the first step. */
+int qs_create(qs_env **out, int variant, int64_t num_envs, int n_gates, const float *gate_pos, const float *gate_yaw,
+              const float *start_pos, int gates_ahead, int device, void *stream);
+int qs_destroy(qs_env *env);
+const char *qs_last_error(const qs_env *env); /* env may be NULL: error of the last failed qs_create */
+
+/* ---- configuration (the reference's attribute pokes, SURVEY.md section 5 "Config / flags") ---------------- */
+int qs_set_stream(qs_env *env, void *stream);
+int qs_set_track_tables(qs_env *env, const float *gate_cos, const float *gate_sin, const float *gate_pos_rel,
+                        const float *gate_yaw_rel);                /* any pointer may be NULL = keep            */
+int qs_get_track_tables(qs_env *env, float *gate_cos, float *gate_sin, float *gate_pos_rel, float *gate_yaw_rel);
+int qs_set_max_steps(qs_env *env, int64_t max_steps);               /* env.max_steps (default 1200, `:345`)      */
+int qs_set_dt(qs_env *env, float dt);                               /* env.dt (default 0.01f, `:346`)            */
+/* env.disturbance_ranges (6,2) rows Mx,My,Mz,Fx,Fy,Fz and env.disturbance_scale (`:355-358`, `:482-489`);
+ * ranges_are_f64: dtype of the array the caller assigned (the training cell assigns float64, `:772-781`) */
+int qs_set_disturbance_ranges(qs_env *env, const double *ranges12, int ranges_are_f64, double scale);
+/* thrust_model.pt / moment_model.pt parameters, row-major [out][in] as torch stores them (`:228-245`) */
+int qs_set_residual_weights(qs_env *env, const float *thrust289, const float *moment451);
+int qs_seed(qs_env *env, uint64_t seed);                            /* device RNG only                           */
+int qs_set_env_offset(qs_env *env, int64_t global_index_of_env0);   /* shard of a multi-GPU job                  */
+int qs_enable_stats(qs_env *env, int on);
+int qs_get_stats(qs_env *env, qs_stats *out, int reset_after_read); /* synchronises                              */
+
+/* ---- state import / export in the reference's layout (host pointers, synchronise) ------------------------- */
+/* world_states (N, state_len) f32, disturbances (N,6) f32 [E2E only], target_gates (N) i64, step_counts (N) i64.
+ * Any pointer may be NULL.  first/count select a slice of envs. */
+int qs_set_state(qs_env *env, int64_t first, int64_t count, const float *world_states, const float *disturbances,
+                 const int64_t *target_gates, const int64_t *step_counts);
+int qs_get_state(qs_env *env, int64_t first, int64_t count, float *world_states, float *disturbances,
+                 int64_t *target_gates, int64_t *step_counts);
+
+/* ---- the hot path (device pointers, asynchronous) ----------------------------------------------------------- */
+/* update_states_gate (`:365-450`): obs_dev (N, obs_len) f32 row-major, 16-byte aligned */
+int qs_observe(qs_env *env, float *obs_dev);
+/* reset() with the device RNG (`:495-496`): redraw every env, zero counters, write the observation */
+int qs_reset_all(qs_env *env, float *obs_dev);
+/* step_async + step_wait (`:498-595`).
+ *   actions_dev (N,4) f32 row-major, 16-byte aligned (the policy's output, clipped to [-1,1] by the caller)
+ *   obs_dev     (N,obs_len) f32   -- MUST be a different buffer from the one returned by the previous call while
+ *                                    the caller still reads it (the reference returns a fresh array every step,
+ *                                    SURVEY.md section 8b "Ownership"); not written in QS_MODE_PAUSE
+ *   rew_dev     (N) f32
+ *   done_dev    (N) u8  0/1
+ *   flags_dev   (N) u8  QS_F_* bits, or NULL */
+int qs_step(qs_env *env, const float *actions_dev, float *obs_dev, float *rew_dev, uint8_t *done_dev,
+            uint8_t *flags_dev, int mode, int reset_source);
+/* second half of a QS_RESET_HOST step: the masked stores of reset_ (`:476-489`) for `count` envs.
+ *   env_index (count) i32 host, ascending; world_states (count,state_len) f32 host; disturbances (count,6) f32
+ *   host or NULL (already multiplied by disturbance_scale).  Zeroes step_counts/target_gates of those envs and
+ *   rewrites their rows of obs_dev.  Synchronises (host inputs). */
+int qs_apply_reset(qs_env *env, int64_t count, const int32_t *env_index, const float *world_states,
+                   const float *disturbances, float *obs_dev);
+
+/* ---- host-buffer convenience: what a NumPy-facing VecEnv calls --------------------------------------------- */
+/* One full step with HOST buffers: copies actions in, steps, copies obs/rew/done(/flags) out, synchronises.
+ * Buffers from qs_host_alloc are pinned and make the copies asynchronous DMA. */
+int qs_step_host(qs_env *env, const float *actions_host, float *obs_host, float *rew_host, uint8_t *done_host,
+                 uint8_t *flags_host, int mode, int reset_source);
+int qs_reset_all_host(qs_env *env, float *obs_host);
+int qs_observe_host(qs_env *env, float *obs_host);
+void *qs_host_alloc(size_t bytes);
+void qs_host_free(void *p);
+
+/* ---- introspection ------------------------------------------------------------------------------------------ */
+/* algorithmic HBM bytes one env-step moves: 189+4*(20+4*ga) E2E, 141+4*(13+4*ga) INDI */
+int qs_algorithmic_bytes_per_env_step(int variant, int gates_ahead);
+/* number of kernel launches issued by this handle so far (bench.py's gpu_launches) */
+uint64_t qs_launch_count(const qs_env *env);
+/* device pointers of the internal planes, for zero-copy consumers: plane 0..3 = world state float4 planes,
+ * 4 = disturbances (Mx,My,Mz,Fz) float4, 5 = disturbances (Fx,Fy) float2, 6 = packed counters u32
+ * (target_gate<<24 | step_count), 7 = episode counter u32 */
+int qs_get_plane_ptr(qs_env *env, int plane, void **dev_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUADSIM_H */

@@ -1,0 +1,487 @@
+// quadsim_capi.cu -- host side of libquadsim.so: the C ABI declared in include/quadsim.h.
+// Owns the device planes, builds the kernel parameter block, launches the sm_100a kernels of quadsim_kernels.cuh.
+// No torch, no Python: plain pointers and sizes only.
+#include "quadsim_kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "quadsim.h"
+
+using qs::Planes;
+using qs::StepParams;
+
+static_assert(sizeof(qs::Stats) == sizeof(qs_stats), "qs_stats layout");
+static_assert(sizeof(StepParams) < 32000, "kernel parameter block too large");
+
+struct qs_env {
+    int variant = 0, device = 0, n_gates = 0, gates_ahead = 0, obs_len = 0, state_len = 0;
+    int64_t n = 0;
+    cudaStream_t stream = nullptr;
+    Planes planes{};
+    float *track_dev = nullptr;
+    qs::Stats *stats_dev = nullptr;
+    bool stats_on = false, have_weights = false, track_dirty = true;
+    std::vector<float> gate_pos, gate_yaw, gate_cos, gate_sin, pos_rel, yaw_rel;
+    float start_pos[3] = {0, 0, 0};
+    double ranges[12] = {0};
+    int ranges_f64 = 0;
+    double dist_scale = 1.0;
+    int64_t max_steps = 1200;
+    float dt = 0.01f;
+    uint64_t seed = 0;
+    int64_t env_offset = 0;
+    StepParams P{};  // weights live here
+    // staging for the host-buffer entry points
+    float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr;
+    uint8_t *h_done = nullptr, *h_flags = nullptr;
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    uint64_t launches = 0;
+    std::string err;
+};
+
+static std::string g_create_error;
+
+#define QS_CHECK_ENV(e) \
+    if (!(e)) return QS_ERR_ARG
+#define QS_CUDA(e, call)                                                                       \
+    do {                                                                                       \
+        cudaError_t _c = (call);                                                               \
+        if (_c != cudaSuccess) {                                                               \
+            (e)->err = std::string(#call) + ": " + cudaGetErrorString(_c);                     \
+            return QS_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+static int fail(qs_env *e, int code, const char *msg) {
+    if (e) e->err = msg; else g_create_error = msg;
+    return code;
+}
+
+extern "C" {
+
+int qs_state_len(int variant) { return variant == QS_E2E ? 16 : 13; }
+int qs_obs_len(int variant, int ga) { return (variant == QS_E2E ? 20 : 13) + 4 * ga; }
+int qs_algorithmic_bytes_per_env_step(int variant, int ga) {
+    return variant == QS_E2E ? 189 + 4 * (20 + 4 * ga) : 141 + 4 * (13 + 4 * ga);
+}
+const char *qs_version(void) { return "quadsim-b200 0.1 (sm_100a)"; }
+const char *qs_last_error(const qs_env *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+uint64_t qs_launch_count(const qs_env *e) { return e ? e->launches : 0; }
+
+static void compute_track_tables(qs_env *e) {
+    // Quadcopter3DGates.__init__ (`3D quad race.ipynb:309-319`): gate i expressed in the frame of gate i-1 (cyclic)
+    const int ng = e->n_gates;
+    e->gate_cos.resize(ng); e->gate_sin.resize(ng); e->pos_rel.resize(3 * ng); e->yaw_rel.resize(ng);
+    for (int i = 0; i < ng; ++i) { e->gate_cos[i] = cosf(e->gate_yaw[i]); e->gate_sin[i] = sinf(e->gate_yaw[i]); }
+    for (int i = 0; i < ng; ++i) {
+        const int j = (i + ng - 1) % ng;
+        const float dx = e->gate_pos[3 * i] - e->gate_pos[3 * j], dy = e->gate_pos[3 * i + 1] - e->gate_pos[3 * j + 1];
+        const float c = e->gate_cos[j], s = e->gate_sin[j];
+        volatile float a = c * dx, b = s * dy, cc = (-s) * dx, d = c * dy;  // separately rounded products
+        e->pos_rel[3 * i] = a + b;
+        e->pos_rel[3 * i + 1] = cc + d;
+        e->pos_rel[3 * i + 2] = e->gate_pos[3 * i + 2] - e->gate_pos[3 * j + 2];
+        e->yaw_rel[i] = e->gate_yaw[i] - e->gate_yaw[j];
+    }
+}
+
+static int upload_track(qs_env *e) {
+    if (!e->track_dirty) return QS_OK;
+    std::vector<float> t((size_t)e->n_gates * qs::kTrackRow, 0.f);
+    for (int g = 0; g < e->n_gates; ++g) {
+        float *r = &t[(size_t)g * qs::kTrackRow];
+        r[0] = e->gate_pos[3 * g]; r[1] = e->gate_pos[3 * g + 1]; r[2] = e->gate_pos[3 * g + 2]; r[3] = e->gate_yaw[g];
+        r[4] = e->gate_cos[g]; r[5] = e->gate_sin[g];
+        r[8] = e->pos_rel[3 * g]; r[9] = e->pos_rel[3 * g + 1]; r[10] = e->pos_rel[3 * g + 2]; r[11] = e->yaw_rel[g];
+    }
+    // stream-ordered with respect to kernels that read the old table
+    QS_CUDA(e, cudaStreamSynchronize(e->stream));
+    QS_CUDA(e, cudaMemcpy(e->track_dev, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+    e->track_dirty = false;
+    return QS_OK;
+}
+
+static void refresh_params(qs_env *e) {
+    StepParams &P = e->P;
+    P.s = e->planes;
+    P.track = e->track_dev;
+    P.stats = e->stats_on ? e->stats_dev : nullptr;
+    P.n = e->n;
+    P.env_offset = e->env_offset;
+    P.seed = e->seed;
+    P.n_gates = e->n_gates;
+    P.gates_ahead = e->gates_ahead;
+    P.obs_len = e->obs_len;
+    P.max_steps = e->max_steps < 0 ? 0u : (e->max_steps > 0xFFFFFF ? 0xFFFFFFFFu : (uint32_t)e->max_steps);
+    P.dt = e->dt;
+    static const int rows[4] = {0, 1, 2, 5};
+    for (int k = 0; k < 4; ++k) {  // 2*(d-lo)/(hi-lo)-1 with the lo==hi widening of `:419-442`
+        double lo = e->ranges[2 * rows[k]], hi = e->ranges[2 * rows[k] + 1];
+        if (lo == hi) { lo -= 1; hi += 1; }
+        P.obs_scale[k] = (float)(2.0 / (hi - lo));
+        P.obs_off[k] = (float)(-2.0 * lo / (hi - lo) - 1.0);
+    }
+    for (int k = 0; k < 3; ++k) P.rd.start[k] = e->start_pos[k];
+    for (int k = 0; k < 6; ++k) {
+        P.rd.dist_lo[k] = (float)(e->dist_scale * e->ranges[2 * k]);
+        P.rd.dist_span[k] = (float)(e->dist_scale * (e->ranges[2 * k + 1] - e->ranges[2 * k]));
+    }
+}
+
+static size_t smem_bytes(const qs_env *e) {
+    return ((size_t)qs::kBlock * e->obs_len + (size_t)e->n_gates * qs::kTrackRow) * sizeof(float);
+}
+static unsigned grid_for(int64_t n) { return (unsigned)((n + qs::kBlock - 1) / qs::kBlock); }
+
+static int ensure_scratch(qs_env *e, size_t bytes) {
+    if (bytes <= e->scratch_bytes) return QS_OK;
+    if (e->scratch) { QS_CUDA(e, cudaStreamSynchronize(e->stream)); cudaFree(e->scratch); e->scratch = nullptr; e->scratch_bytes = 0; }
+    QS_CUDA(e, cudaMalloc(&e->scratch, bytes));
+    e->scratch_bytes = bytes;
+    return QS_OK;
+}
+
+int qs_create(qs_env **out, int variant, int64_t num_envs, int n_gates, const float *gate_pos, const float *gate_yaw,
+              const float *start_pos, int gates_ahead, int device, void *stream) {
+    if (!out) return fail(nullptr, QS_ERR_ARG, "qs_create: out is NULL");
+    *out = nullptr;
+    if (variant != QS_E2E && variant != QS_INDI) return fail(nullptr, QS_ERR_ARG, "qs_create: unknown variant");
+    if (num_envs <= 0 || num_envs > (int64_t)1 << 31) return fail(nullptr, QS_ERR_ARG, "qs_create: num_envs out of range");
+    if (n_gates <= 0 || n_gates > QS_MAX_GATES) return fail(nullptr, QS_ERR_ARG, "qs_create: n_gates must be 1..255");
+    if (gates_ahead < 0 || gates_ahead > 16) return fail(nullptr, QS_ERR_ARG, "qs_create: gates_ahead must be 0..16");
+    if (!gate_pos || !gate_yaw || !start_pos) return fail(nullptr, QS_ERR_ARG, "qs_create: NULL track pointer");
+    qs_env *e = new (std::nothrow) qs_env();
+    if (!e) return fail(nullptr, QS_ERR_NOMEM, "qs_create: out of host memory");
+    e->variant = variant; e->device = device; e->n = num_envs; e->n_gates = n_gates; e->gates_ahead = gates_ahead;
+    e->state_len = qs_state_len(variant); e->obs_len = qs_obs_len(variant, gates_ahead);
+    e->stream = (cudaStream_t)stream;
+    e->gate_pos.assign(gate_pos, gate_pos + 3 * n_gates);
+    e->gate_yaw.assign(gate_yaw, gate_yaw + n_gates);
+    memcpy(e->start_pos, start_pos, sizeof e->start_pos);
+    compute_track_tables(e);
+
+    auto bail = [&](cudaError_t c, const char *what) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(c);
+        qs_destroy(e);
+        return (int)QS_ERR_CUDA;
+    };
+    cudaError_t c;
+    if ((c = cudaSetDevice(device)) != cudaSuccess) return bail(c, "cudaSetDevice");
+    const size_t n = (size_t)num_envs;
+    Planes &s = e->planes;
+    if ((c = cudaMalloc(&s.p0, n * 16)) != cudaSuccess) return bail(c, "cudaMalloc");
+    if ((c = cudaMalloc(&s.p1, n * 16)) != cudaSuccess) return bail(c, "cudaMalloc");
+    if ((c = cudaMalloc(&s.p2, n * 16)) != cudaSuccess) return bail(c, "cudaMalloc");
+    if (variant == QS_E2E) {
+        if ((c = cudaMalloc(&s.p3, n * 16)) != cudaSuccess) return bail(c, "cudaMalloc");
+        if ((c = cudaMalloc(&s.da, n * 16)) != cudaSuccess) return bail(c, "cudaMalloc");
+        if ((c = cudaMalloc(&s.db, n * 8)) != cudaSuccess) return bail(c, "cudaMalloc");
+        cudaMemset(s.p3, 0, n * 16); cudaMemset(s.da, 0, n * 16); cudaMemset(s.db, 0, n * 8);
+    } else {
+        if ((c = cudaMalloc(&s.p3s, n * 4)) != cudaSuccess) return bail(c, "cudaMalloc");
+        cudaMemset(s.p3s, 0, n * 4);
+    }
+    if ((c = cudaMalloc(&s.meta, n * 4)) != cudaSuccess) return bail(c, "cudaMalloc");
+    if ((c = cudaMalloc(&s.episode, n * 4)) != cudaSuccess) return bail(c, "cudaMalloc");
+    cudaMemset(s.p0, 0, n * 16); cudaMemset(s.p1, 0, n * 16); cudaMemset(s.p2, 0, n * 16);
+    cudaMemset(s.meta, 0, n * 4); cudaMemset(s.episode, 0, n * 4);
+    if ((c = cudaMalloc(&e->track_dev, (size_t)n_gates * qs::kTrackRow * 4)) != cudaSuccess) return bail(c, "cudaMalloc");
+    if ((c = cudaMalloc(&e->stats_dev, sizeof(qs::Stats))) != cudaSuccess) return bail(c, "cudaMalloc");
+    cudaMemset(e->stats_dev, 0, sizeof(qs::Stats));
+    if ((c = cudaDeviceSynchronize()) != cudaSuccess) return bail(c, "cudaDeviceSynchronize");
+    // the observation tile + track table must fit in dynamic shared memory
+    const size_t smem = smem_bytes(e);
+    if (smem > 48 * 1024) {
+        const void *fns[] = {(const void *)qs::step_kernel<qs::kE2E>, (const void *)qs::step_kernel<qs::kINDI>,
+                             (const void *)qs::observe_kernel<qs::kE2E>, (const void *)qs::observe_kernel<qs::kINDI>,
+                             (const void *)qs::apply_reset_kernel<qs::kE2E>, (const void *)qs::apply_reset_kernel<qs::kINDI>};
+        for (const void *f : fns)
+            if ((c = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+                return bail(c, "cudaFuncSetAttribute(smem)");
+    }
+    *out = e;
+    return QS_OK;
+}
+
+int qs_destroy(qs_env *e) {
+    if (!e) return QS_OK;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream); else cudaDeviceSynchronize();
+    Planes &s = e->planes;
+    cudaFree(s.p0); cudaFree(s.p1); cudaFree(s.p2); cudaFree(s.p3); cudaFree(s.p3s); cudaFree(s.da); cudaFree(s.db);
+    cudaFree(s.meta); cudaFree(s.episode); cudaFree(e->track_dev); cudaFree(e->stats_dev); cudaFree(e->scratch);
+    cudaFree(e->h_act); cudaFree(e->h_obs); cudaFree(e->h_rew); cudaFree(e->h_done); cudaFree(e->h_flags);
+    delete e;
+    return QS_OK;
+}
+
+int qs_set_stream(qs_env *e, void *stream) { QS_CHECK_ENV(e); e->stream = (cudaStream_t)stream; return QS_OK; }
+
+int qs_set_track_tables(qs_env *e, const float *gc, const float *gs, const float *pr, const float *yr) {
+    QS_CHECK_ENV(e);
+    const int ng = e->n_gates;
+    if (gc) e->gate_cos.assign(gc, gc + ng);
+    if (gs) e->gate_sin.assign(gs, gs + ng);
+    if (pr) e->pos_rel.assign(pr, pr + 3 * ng);
+    if (yr) e->yaw_rel.assign(yr, yr + ng);
+    e->track_dirty = true;
+    return QS_OK;
+}
+
+int qs_get_track_tables(qs_env *e, float *gc, float *gs, float *pr, float *yr) {
+    QS_CHECK_ENV(e);
+    const int ng = e->n_gates;
+    if (gc) memcpy(gc, e->gate_cos.data(), ng * 4);
+    if (gs) memcpy(gs, e->gate_sin.data(), ng * 4);
+    if (pr) memcpy(pr, e->pos_rel.data(), 3 * ng * 4);
+    if (yr) memcpy(yr, e->yaw_rel.data(), ng * 4);
+    return QS_OK;
+}
+
+int qs_set_max_steps(qs_env *e, int64_t m) { QS_CHECK_ENV(e); e->max_steps = m; return QS_OK; }
+int qs_set_dt(qs_env *e, float dt) { QS_CHECK_ENV(e); e->dt = dt; return QS_OK; }
+int qs_seed(qs_env *e, uint64_t seed) { QS_CHECK_ENV(e); e->seed = seed; return QS_OK; }
+int qs_set_env_offset(qs_env *e, int64_t off) { QS_CHECK_ENV(e); e->env_offset = off; return QS_OK; }
+
+int qs_set_disturbance_ranges(qs_env *e, const double *r, int is_f64, double scale) {
+    QS_CHECK_ENV(e);
+    if (!r) return fail(e, QS_ERR_ARG, "qs_set_disturbance_ranges: NULL");
+    if (e->variant != QS_E2E) return fail(e, QS_ERR_STATE, "disturbances exist only in the E2E variant");
+    memcpy(e->ranges, r, sizeof e->ranges);
+    e->ranges_f64 = is_f64;
+    e->dist_scale = scale;
+    return QS_OK;
+}
+
+int qs_set_residual_weights(qs_env *e, const float *t, const float *m) {
+    QS_CHECK_ENV(e);
+    if (!t || !m) return fail(e, QS_ERR_ARG, "qs_set_residual_weights: NULL");
+    if (e->variant != QS_E2E) return fail(e, QS_ERR_STATE, "residual MLPs exist only in the E2E variant");
+    memcpy(e->P.wt, t, sizeof e->P.wt);
+    memcpy(e->P.wm, m, sizeof e->P.wm);
+    e->have_weights = true;
+    return QS_OK;
+}
+
+int qs_enable_stats(qs_env *e, int on) { QS_CHECK_ENV(e); e->stats_on = on != 0; return QS_OK; }
+
+int qs_get_stats(qs_env *e, qs_stats *out, int reset) {
+    QS_CHECK_ENV(e);
+    if (!out) return fail(e, QS_ERR_ARG, "qs_get_stats: NULL");
+    QS_CUDA(e, cudaSetDevice(e->device));
+    QS_CUDA(e, cudaMemcpyAsync(out, e->stats_dev, sizeof(qs_stats), cudaMemcpyDeviceToHost, e->stream));
+    if (reset) QS_CUDA(e, cudaMemsetAsync(e->stats_dev, 0, sizeof(qs_stats), e->stream));
+    QS_CUDA(e, cudaStreamSynchronize(e->stream));
+    return QS_OK;
+}
+
+int qs_get_plane_ptr(qs_env *e, int plane, void **p) {
+    QS_CHECK_ENV(e);
+    if (!p) return fail(e, QS_ERR_ARG, "qs_get_plane_ptr: NULL");
+    const Planes &s = e->planes;
+    void *tab[8] = {s.p0, s.p1, s.p2, e->variant == QS_E2E ? (void *)s.p3 : (void *)s.p3s, s.da, s.db, s.meta, s.episode};
+    if (plane < 0 || plane > 7) return fail(e, QS_ERR_ARG, "qs_get_plane_ptr: plane must be 0..7");
+    *p = tab[plane];
+    return QS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- state import / export
+static int check_slice(qs_env *e, int64_t first, int64_t count) {
+    if (first < 0 || count < 0 || first + count > e->n) return fail(e, QS_ERR_ARG, "env slice out of range");
+    return QS_OK;
+}
+
+int qs_set_state(qs_env *e, int64_t first, int64_t count, const float *ws, const float *dist, const int64_t *tg,
+                 const int64_t *sc) {
+    QS_CHECK_ENV(e);
+    if (int r = check_slice(e, first, count)) return r;
+    if (dist && e->variant != QS_E2E) return fail(e, QS_ERR_STATE, "disturbances exist only in the E2E variant");
+    if (count == 0) return QS_OK;
+    QS_CUDA(e, cudaSetDevice(e->device));
+    const size_t b_ws = ws ? (size_t)count * e->state_len * 4 : 0, b_d = dist ? (size_t)count * 24 : 0;
+    const size_t b_tg = tg ? (size_t)count * 8 : 0, b_sc = sc ? (size_t)count * 8 : 0;
+    if (int r = ensure_scratch(e, b_ws + b_d + b_tg + b_sc + 64)) return r;
+    char *base = (char *)e->scratch;
+    float *d_ws = (float *)base; float *d_d = (float *)(base + b_ws);
+    long long *d_tg = (long long *)(base + b_ws + b_d), *d_sc = (long long *)(base + b_ws + b_d + b_tg);
+    if (ws) QS_CUDA(e, cudaMemcpyAsync(d_ws, ws, b_ws, cudaMemcpyHostToDevice, e->stream));
+    if (dist) QS_CUDA(e, cudaMemcpyAsync(d_d, dist, b_d, cudaMemcpyHostToDevice, e->stream));
+    if (tg) QS_CUDA(e, cudaMemcpyAsync(d_tg, tg, b_tg, cudaMemcpyHostToDevice, e->stream));
+    if (sc) QS_CUDA(e, cudaMemcpyAsync(d_sc, sc, b_sc, cudaMemcpyHostToDevice, e->stream));
+    const unsigned grid = (unsigned)((count + 255) / 256);
+    if (e->variant == QS_E2E)
+        qs::import_kernel<qs::kE2E><<<grid, 256, 0, e->stream>>>(e->planes, first, count, ws ? d_ws : nullptr,
+                                                               dist ? d_d : nullptr, tg ? d_tg : nullptr,
+                                                               sc ? d_sc : nullptr, e->n_gates);
+    else
+        qs::import_kernel<qs::kINDI><<<grid, 256, 0, e->stream>>>(e->planes, first, count, ws ? d_ws : nullptr, nullptr,
+                                                                tg ? d_tg : nullptr, sc ? d_sc : nullptr, e->n_gates);
+    e->launches++;
+    QS_CUDA(e, cudaGetLastError());
+    QS_CUDA(e, cudaStreamSynchronize(e->stream));
+    return QS_OK;
+}
+
+int qs_get_state(qs_env *e, int64_t first, int64_t count, float *ws, float *dist, int64_t *tg, int64_t *sc) {
+    QS_CHECK_ENV(e);
+    if (int r = check_slice(e, first, count)) return r;
+    if (dist && e->variant != QS_E2E) return fail(e, QS_ERR_STATE, "disturbances exist only in the E2E variant");
+    if (count == 0) return QS_OK;
+    QS_CUDA(e, cudaSetDevice(e->device));
+    const size_t b_ws = ws ? (size_t)count * e->state_len * 4 : 0, b_d = dist ? (size_t)count * 24 : 0;
+    const size_t b_tg = tg ? (size_t)count * 8 : 0, b_sc = sc ? (size_t)count * 8 : 0;
+    if (int r = ensure_scratch(e, b_ws + b_d + b_tg + b_sc + 64)) return r;
+    char *base = (char *)e->scratch;
+    float *d_ws = (float *)base; float *d_d = (float *)(base + b_ws);
+    long long *d_tg = (long long *)(base + b_ws + b_d), *d_sc = (long long *)(base + b_ws + b_d + b_tg);
+    const unsigned grid = (unsigned)((count + 255) / 256);
+    if (e->variant == QS_E2E)
+        qs::export_kernel<qs::kE2E><<<grid, 256, 0, e->stream>>>(e->planes, first, count, ws ? d_ws : nullptr,
+                                                               dist ? d_d : nullptr, tg ? d_tg : nullptr,
+                                                               sc ? d_sc : nullptr);
+    else
+        qs::export_kernel<qs::kINDI><<<grid, 256, 0, e->stream>>>(e->planes, first, count, ws ? d_ws : nullptr, nullptr,
+                                                                tg ? d_tg : nullptr, sc ? d_sc : nullptr);
+    e->launches++;
+    QS_CUDA(e, cudaGetLastError());
+    if (ws) QS_CUDA(e, cudaMemcpyAsync(ws, d_ws, b_ws, cudaMemcpyDeviceToHost, e->stream));
+    if (dist) QS_CUDA(e, cudaMemcpyAsync(dist, d_d, b_d, cudaMemcpyDeviceToHost, e->stream));
+    if (tg) QS_CUDA(e, cudaMemcpyAsync(tg, d_tg, b_tg, cudaMemcpyDeviceToHost, e->stream));
+    if (sc) QS_CUDA(e, cudaMemcpyAsync(sc, d_sc, b_sc, cudaMemcpyDeviceToHost, e->stream));
+    QS_CUDA(e, cudaStreamSynchronize(e->stream));
+    return QS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- hot path
+static int prep_launch(qs_env *e, const char *who) {
+    if (e->variant == QS_E2E && !e->have_weights) {
+        e->err = std::string(who) + ": residual MLP weights not set (qs_set_residual_weights)";
+        return QS_ERR_STATE;
+    }
+    QS_CUDA(e, cudaSetDevice(e->device));
+    if (int r = upload_track(e)) return r;
+    refresh_params(e);
+    return QS_OK;
+}
+
+static int launch_observe(qs_env *e, float *obs_dev, int reset_all, const char *who) {
+    if (!obs_dev) return fail(e, QS_ERR_ARG, "obs_dev is NULL");
+    if (int r = prep_launch(e, who)) return r;
+    e->P.obs = obs_dev;
+    if (e->variant == QS_E2E)
+        qs::observe_kernel<qs::kE2E><<<grid_for(e->n), qs::kBlock, smem_bytes(e), e->stream>>>(e->P, reset_all);
+    else
+        qs::observe_kernel<qs::kINDI><<<grid_for(e->n), qs::kBlock, smem_bytes(e), e->stream>>>(e->P, reset_all);
+    e->launches++;
+    QS_CUDA(e, cudaGetLastError());
+    return QS_OK;
+}
+
+int qs_observe(qs_env *e, float *obs_dev) { QS_CHECK_ENV(e); return launch_observe(e, obs_dev, 0, "qs_observe"); }
+int qs_reset_all(qs_env *e, float *obs_dev) { QS_CHECK_ENV(e); return launch_observe(e, obs_dev, 1, "qs_reset_all"); }
+
+int qs_step(qs_env *e, const float *actions_dev, float *obs_dev, float *rew_dev, uint8_t *done_dev, uint8_t *flags_dev,
+            int mode, int reset_source) {
+    QS_CHECK_ENV(e);
+    if (!actions_dev || !rew_dev || !done_dev) return fail(e, QS_ERR_ARG, "qs_step: NULL buffer");
+    if (mode < QS_MODE_NORMAL || mode > QS_MODE_PAUSE) return fail(e, QS_ERR_ARG, "qs_step: bad mode");
+    if (reset_source != QS_RESET_DEVICE && reset_source != QS_RESET_HOST) return fail(e, QS_ERR_ARG, "qs_step: bad reset_source");
+    if (mode != QS_MODE_PAUSE && !obs_dev) return fail(e, QS_ERR_ARG, "qs_step: obs_dev is NULL");
+    if ((uintptr_t)actions_dev & 15) return fail(e, QS_ERR_ARG, "qs_step: actions_dev must be 16-byte aligned");
+    if (int r = prep_launch(e, "qs_step")) return r;
+    StepParams &P = e->P;
+    P.actions = reinterpret_cast<const float4 *>(actions_dev);
+    P.obs = obs_dev; P.rew = rew_dev; P.done = done_dev; P.flags = flags_dev;
+    P.mode = mode; P.reset_source = reset_source;
+    if (e->variant == QS_E2E)
+        qs::step_kernel<qs::kE2E><<<grid_for(e->n), qs::kBlock, smem_bytes(e), e->stream>>>(P);
+    else
+        qs::step_kernel<qs::kINDI><<<grid_for(e->n), qs::kBlock, smem_bytes(e), e->stream>>>(P);
+    e->launches++;
+    QS_CUDA(e, cudaGetLastError());
+    return QS_OK;
+}
+
+int qs_apply_reset(qs_env *e, int64_t count, const int32_t *idx, const float *ws, const float *dist, float *obs_dev) {
+    QS_CHECK_ENV(e);
+    if (count == 0) return QS_OK;
+    if (count < 0 || count > e->n || !idx || !ws || !obs_dev) return fail(e, QS_ERR_ARG, "qs_apply_reset: bad argument");
+    if (dist && e->variant != QS_E2E) return fail(e, QS_ERR_STATE, "disturbances exist only in the E2E variant");
+    for (int64_t k = 0; k < count; ++k)
+        if (idx[k] < 0 || idx[k] >= e->n) return fail(e, QS_ERR_ARG, "qs_apply_reset: env index out of range");
+    if (int r = prep_launch(e, "qs_apply_reset")) return r;
+    const size_t b_i = ((size_t)count * 4 + 15) & ~(size_t)15, b_ws = (size_t)count * e->state_len * 4;
+    const size_t b_d = dist ? (size_t)count * 24 : 0;
+    if (int r = ensure_scratch(e, b_i + b_ws + b_d + 64)) return r;
+    char *base = (char *)e->scratch;
+    int *d_i = (int *)base; float *d_ws = (float *)(base + b_i); float *d_d = (float *)(base + b_i + b_ws);
+    QS_CUDA(e, cudaMemcpyAsync(d_i, idx, (size_t)count * 4, cudaMemcpyHostToDevice, e->stream));
+    QS_CUDA(e, cudaMemcpyAsync(d_ws, ws, b_ws, cudaMemcpyHostToDevice, e->stream));
+    if (dist) QS_CUDA(e, cudaMemcpyAsync(d_d, dist, b_d, cudaMemcpyHostToDevice, e->stream));
+    e->P.obs = obs_dev;
+    if (e->variant == QS_E2E)
+        qs::apply_reset_kernel<qs::kE2E><<<grid_for(count), qs::kBlock, smem_bytes(e), e->stream>>>(e->P, count, d_i, d_ws,
+                                                                                                 dist ? d_d : nullptr);
+    else
+        qs::apply_reset_kernel<qs::kINDI><<<grid_for(count), qs::kBlock, smem_bytes(e), e->stream>>>(e->P, count, d_i, d_ws,
+                                                                                                  nullptr);
+    e->launches++;
+    QS_CUDA(e, cudaGetLastError());
+    QS_CUDA(e, cudaStreamSynchronize(e->stream));
+    return QS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- host-buffer entry points
+static int ensure_io(qs_env *e) {
+    if (e->h_act) return QS_OK;
+    const size_t n = (size_t)e->n;
+    QS_CUDA(e, cudaSetDevice(e->device));
+    QS_CUDA(e, cudaMalloc(&e->h_act, n * 16));
+    QS_CUDA(e, cudaMalloc(&e->h_obs, n * e->obs_len * 4));
+    QS_CUDA(e, cudaMalloc(&e->h_rew, n * 4));
+    QS_CUDA(e, cudaMalloc(&e->h_done, n));
+    QS_CUDA(e, cudaMalloc(&e->h_flags, n));
+    return QS_OK;
+}
+
+int qs_step_host(qs_env *e, const float *act, float *obs, float *rew, uint8_t *done, uint8_t *flags, int mode,
+                 int reset_source) {
+    QS_CHECK_ENV(e);
+    if (!act || !rew || !done) return fail(e, QS_ERR_ARG, "qs_step_host: NULL buffer");
+    if (int r = ensure_io(e)) return r;
+    const size_t n = (size_t)e->n;
+    QS_CUDA(e, cudaMemcpyAsync(e->h_act, act, n * 16, cudaMemcpyHostToDevice, e->stream));
+    if (int r = qs_step(e, e->h_act, e->h_obs, e->h_rew, e->h_done, flags ? e->h_flags : nullptr, mode, reset_source)) return r;
+    if (obs && mode != QS_MODE_PAUSE)
+        QS_CUDA(e, cudaMemcpyAsync(obs, e->h_obs, n * e->obs_len * 4, cudaMemcpyDeviceToHost, e->stream));
+    QS_CUDA(e, cudaMemcpyAsync(rew, e->h_rew, n * 4, cudaMemcpyDeviceToHost, e->stream));
+    QS_CUDA(e, cudaMemcpyAsync(done, e->h_done, n, cudaMemcpyDeviceToHost, e->stream));
+    if (flags) QS_CUDA(e, cudaMemcpyAsync(flags, e->h_flags, n, cudaMemcpyDeviceToHost, e->stream));
+    QS_CUDA(e, cudaStreamSynchronize(e->stream));
+    return QS_OK;
+}
+
+static int observe_host(qs_env *e, float *obs, int reset_all) {
+    if (!obs) return fail(e, QS_ERR_ARG, "obs_host is NULL");
+    if (int r = ensure_io(e)) return r;
+    if (int r = launch_observe(e, e->h_obs, reset_all, reset_all ? "qs_reset_all_host" : "qs_observe_host")) return r;
+    QS_CUDA(e, cudaMemcpyAsync(obs, e->h_obs, (size_t)e->n * e->obs_len * 4, cudaMemcpyDeviceToHost, e->stream));
+    QS_CUDA(e, cudaStreamSynchronize(e->stream));
+    return QS_OK;
+}
+int qs_reset_all_host(qs_env *e, float *obs) { QS_CHECK_ENV(e); return observe_host(e, obs, 1); }
+int qs_observe_host(qs_env *e, float *obs) { QS_CHECK_ENV(e); return observe_host(e, obs, 0); }
+
+void *qs_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
+}
+void qs_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

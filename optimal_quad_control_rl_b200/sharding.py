@@ -1,0 +1,43 @@
+"""Multi-GPU: envs are independent, so a job of N quads is N/G contiguous envs per rank with NO data-path
+collective.  The one optional exchange is the all-gather of observations for a policy that lives on one rank
+(BASELINE.json config 4); the step kernel writes its tile straight into this rank's slice of the gather buffer,
+so the collective needs no staging copy (NCCL in-place all-gather)."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total_envs: int, rank: int, world_size: int):
+    """Contiguous block [first, first+count) of rank; remainders go to the low ranks."""
+    base, rem = divmod(int(total_envs), int(world_size))
+    count = base + (1 if rank < rem else 0)
+    first = rank * base + min(rank, rem)
+    return first, count
+
+
+class ObsAllGather:
+    """Pre-allocated (total_envs, D) buffer; ``local_slot()`` is where this rank's step writes its observations."""
+
+    def __init__(self, total_envs, obs_len, device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.first, self.count = shard_range(total_envs, self.rank, self.world)
+        self.equal = total_envs % self.world == 0
+        self.buf = torch.zeros((total_envs, obs_len), dtype=torch.float32, device=device)
+
+    def local_slot(self):
+        return self.buf[self.first:self.first + self.count]
+
+    def gather(self):
+        """All ranks end with every rank's observations in ``buf``."""
+        if self.world == 1:
+            return self.buf
+        if self.equal:
+            dist.all_gather_into_tensor(self.buf, self.local_slot(), group=self.group)
+        else:  # ragged shards: list form
+            outs = [self.buf[f:f + c] for f, c in (shard_range(self.buf.shape[0], r, self.world)
+                                                    for r in range(self.world))]
+            dist.all_gather(outs, self.local_slot().contiguous(), group=self.group)
+        return self.buf
