@@ -240,9 +240,15 @@ def run_ours(a):
     lib = env._lib
     D = env.state_len
     import ctypes as C
-    pin = lambda nbytes: lib.qs_host_alloc(nbytes)
+    def pin(nbytes):
+        p = lib.qs_host_alloc(nbytes)
+        if not p:
+            raise SystemExit('qs_host_alloc failed')
+        return p
+
     h_act, h_obs, h_rew, h_done = pin(n * 16), pin(n * D * 4), pin(n * 4), pin(n)
-    C.memmove(h_act, acts[0].cpu().numpy().ctypes.data, n * 16)
+    src = acts[0].cpu().numpy()
+    C.memmove(C.c_void_p(h_act), C.c_void_p(src.ctypes.data), n * 16)
     ke = max(a.e2e_steps, 3)
     for _ in range(3):
         env._call("qs_step_host", h_act, h_obs, h_rew, h_done, None, L.MODE_NORMAL, L.RESET_DEVICE)

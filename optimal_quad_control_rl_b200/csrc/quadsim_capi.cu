@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -42,6 +43,8 @@ struct qs_env {
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
     uint64_t launches = 0;
+    int stages = 2, step_grid = 0;  // pipeline depth and persistent grid of the step kernel
+    size_t step_smem = 0;
     std::string err;
 };
 
@@ -134,6 +137,15 @@ static void refresh_params(qs_env *e) {
     }
 }
 
+static const void *step_function(const qs_env *e) {
+    const bool e2e = e->variant == QS_E2E;
+    switch (e->stages) {
+        case 3: return e2e ? (const void *)qs::step_kernel<qs::kE2E, 3> : (const void *)qs::step_kernel<qs::kINDI, 3>;
+        case 4: return e2e ? (const void *)qs::step_kernel<qs::kE2E, 4> : (const void *)qs::step_kernel<qs::kINDI, 4>;
+        default: return e2e ? (const void *)qs::step_kernel<qs::kE2E, 2> : (const void *)qs::step_kernel<qs::kINDI, 2>;
+    }
+}
+
 static size_t smem_bytes(const qs_env *e) {
     return ((size_t)qs::kBlock * e->obs_len + (size_t)e->n_gates * qs::kTrackRow) * sizeof(float);
 }
@@ -173,7 +185,8 @@ int qs_create(qs_env **out, int variant, int64_t num_envs, int n_gates, const fl
     };
     cudaError_t c;
     if ((c = cudaSetDevice(device)) != cudaSuccess) return bail(c, "cudaSetDevice");
-    const size_t n = (size_t)num_envs;
+    // planes are padded to whole 128-env tiles (zero-filled) so that every bulk load of the step kernel is full-size
+    const size_t n = ((size_t)num_envs + qs::kBlock - 1) / qs::kBlock * qs::kBlock;
     Planes &s = e->planes;
     if ((c = cudaMalloc(&s.p0, n * 16)) != cudaSuccess) return bail(c, "cudaMalloc");
     if ((c = cudaMalloc(&s.p1, n * 16)) != cudaSuccess) return bail(c, "cudaMalloc");
@@ -198,13 +211,27 @@ int qs_create(qs_env **out, int variant, int64_t num_envs, int n_gates, const fl
     // the observation tile + track table must fit in dynamic shared memory
     const size_t smem = smem_bytes(e);
     if (smem > 48 * 1024) {
-        const void *fns[] = {(const void *)qs::step_kernel<qs::kE2E>, (const void *)qs::step_kernel<qs::kINDI>,
-                             (const void *)qs::observe_kernel<qs::kE2E>, (const void *)qs::observe_kernel<qs::kINDI>,
+        const void *fns[] = {(const void *)qs::observe_kernel<qs::kE2E>, (const void *)qs::observe_kernel<qs::kINDI>,
                              (const void *)qs::apply_reset_kernel<qs::kE2E>, (const void *)qs::apply_reset_kernel<qs::kINDI>};
         for (const void *f : fns)
             if ((c = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
                 return bail(c, "cudaFuncSetAttribute(smem)");
     }
+    // persistent step kernel: pipeline depth, shared memory, grid = SMs x resident CTAs
+    if (const char *sv = getenv("QS_STAGES")) e->stages = atoi(sv) == 3 ? 3 : (atoi(sv) == 4 ? 4 : 2);
+    const void *step_fn = step_function(e);
+    e->step_smem = qs::step_smem_bytes(variant, e->stages, e->obs_len, n_gates);
+    if ((c = cudaFuncSetAttribute(step_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem)) != cudaSuccess)
+        return bail(c, "cudaFuncSetAttribute(step smem)");
+    int per_sm = 0, sms = 0;
+    if ((c = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_fn, qs::kBlock, e->step_smem)) != cudaSuccess)
+        return bail(c, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    if ((c = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
+        return bail(c, "cudaDeviceGetAttribute");
+    if (per_sm < 1) { g_create_error = "step kernel does not fit on an SM (gates_ahead / n_gates too large)"; qs_destroy(e); return QS_ERR_ARG; }
+    if (const char *cv = getenv("QS_CTAS_PER_SM")) { int v = atoi(cv); if (v >= 1 && v < per_sm) per_sm = v; }
+    const long long tiles = (num_envs + qs::kBlock - 1) / qs::kBlock;
+    e->step_grid = (int)(tiles < (long long)sms * per_sm ? tiles : (long long)sms * per_sm);
     *out = e;
     return QS_OK;
 }
@@ -263,8 +290,17 @@ int qs_set_residual_weights(qs_env *e, const float *t, const float *m) {
     QS_CHECK_ENV(e);
     if (!t || !m) return fail(e, QS_ERR_ARG, "qs_set_residual_weights: NULL");
     if (e->variant != QS_E2E) return fail(e, QS_ERR_STATE, "residual MLPs exist only in the E2E variant");
-    memcpy(e->P.wt, t, sizeof e->P.wt);
-    memcpy(e->P.wm, m, sizeof e->P.wm);
+    // torch layout (row-major [out][in], then bias) -> kernel layout (layer 1 transposed to [in][hidden])
+    StepParams &P = e->P;
+    for (int j = 0; j < 32; ++j) {
+        for (int k = 0; k < 7; ++k) P.wt1[k * 32 + j] = t[j * 7 + k];
+        for (int k = 0; k < 10; ++k) P.wm1[k * 32 + j] = m[j * 10 + k];
+        P.bt1[j] = t[224 + j];
+        P.wt2[j] = t[256 + j];
+        P.bm1[j] = m[320 + j];
+    }
+    memcpy(P.wm2, m + 352, 96 * sizeof(float));
+    P.b2[0] = t[288]; P.b2[1] = m[448]; P.b2[2] = m[449]; P.b2[3] = m[450];
     e->have_weights = true;
     return QS_OK;
 }
@@ -399,10 +435,9 @@ int qs_step(qs_env *e, const float *actions_dev, float *obs_dev, float *rew_dev,
     P.actions = reinterpret_cast<const float4 *>(actions_dev);
     P.obs = obs_dev; P.rew = rew_dev; P.done = done_dev; P.flags = flags_dev;
     P.mode = mode; P.reset_source = reset_source;
-    if (e->variant == QS_E2E)
-        qs::step_kernel<qs::kE2E><<<grid_for(e->n), qs::kBlock, smem_bytes(e), e->stream>>>(P);
-    else
-        qs::step_kernel<qs::kINDI><<<grid_for(e->n), qs::kBlock, smem_bytes(e), e->stream>>>(P);
+    void *args[] = {&P};
+    QS_CUDA(e, cudaLaunchKernel(step_function(e), dim3((unsigned)e->step_grid), dim3(qs::kBlock), args, e->step_smem,
+                                e->stream));
     e->launches++;
     QS_CUDA(e, cudaGetLastError());
     return QS_OK;

@@ -68,8 +68,15 @@ struct StepParams {
     float dt;
     float obs_scale[4], obs_off[4];  // disturbance observation: d*scale+off  (`:414-448`)
     ResetDist rd;
-    float wt[289];  // thrust MLP  W1[32][7] b1[32] W2[32] b2
-    float wm[451];  // moment MLP  W1[32][10] b1[32] W2[3][32] b2[3]
+    // residual MLPs in KERNEL layout (qs_set_residual_weights transposes): layer 1 is [in][hidden] so that two
+    // adjacent hidden units form one 64-bit constant-bank operand of a packed FFMA2
+    alignas(16) float wt1[7 * 32];   // thrust  W1^T
+    alignas(16) float bt1[32];
+    alignas(16) float wt2[32];       // thrust  W2 (1x32)
+    alignas(16) float wm1[10 * 32];  // moment  W1^T
+    alignas(16) float bm1[32];
+    alignas(16) float wm2[3 * 32];   // moment  W2 (3x32)
+    alignas(16) float b2[4];         // thrust b2, moment b2[3]
 };
 
 // ------------------------------------------------------------------------------------------------ small helpers
@@ -160,34 +167,79 @@ __device__ __forceinline__ void store_dist(const Planes &s, long long i, const E
 }
 
 // reset_ (`:452-489`) with the device RNG: same fields, same ranges, counter-based instead of MT19937.
+// Draw c of env g in episode ep is Philox4x32-10(counter=(g_lo,g_hi,ep,c), key=seed): 6 draws (E2E) / 4 (INDI).
+template <int V> struct ResetDraws { enum : int { N = (V == kE2E ? 6 : 4) }; };
+
+__device__ __forceinline__ uint4 reset_draw(const StepParams &P, unsigned long long g, uint32_t episode, uint32_t c) {
+    return philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), episode, c),
+                         make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
+}
+
+template <int V>
+__device__ __forceinline__ void fill_reset(const StepParams &P, const uint4 (&r)[6], EnvState<V> &e) {
+    const float pi = 3.14159265358979f, pi9 = 0.349065850398866f;
+    e.x = P.rd.start[0] + uni(r[0].x, -0.5f, 1.0f);
+    e.y = P.rd.start[1] + uni(r[0].y, -0.5f, 1.0f);
+    e.z = P.rd.start[2] + uni(r[0].z, -0.5f, 1.0f);
+    e.vx = uni(r[0].w, -0.5f, 1.0f); e.vy = uni(r[1].x, -0.5f, 1.0f); e.vz = uni(r[1].y, -0.5f, 1.0f);
+    e.phi = uni(r[1].z, -pi9, 2 * pi9); e.th = uni(r[1].w, -pi9, 2 * pi9); e.psi = uni(r[2].x, -pi, 2 * pi);
+    e.p = uni(r[2].y, -0.1f, 0.2f); e.q = uni(r[2].z, -0.1f, 0.2f); e.r = uni(r[2].w, -0.1f, 0.2f);
+    if (V == kE2E) {
+        e.w[0] = uni(r[3].x, -1.f, 2.f); e.w[1] = uni(r[3].y, -1.f, 2.f);
+        e.w[2] = uni(r[3].z, -1.f, 2.f); e.w[V == kE2E ? 3 : 0] = uni(r[3].w, -1.f, 2.f);
+        e.dist[0] = uni(r[4].x, P.rd.dist_lo[0], P.rd.dist_span[0]);
+        e.dist[1] = uni(r[4].y, P.rd.dist_lo[1], P.rd.dist_span[1]);
+        e.dist[2] = uni(r[4].z, P.rd.dist_lo[2], P.rd.dist_span[2]);
+        e.dist[3] = uni(r[4].w, P.rd.dist_lo[3], P.rd.dist_span[3]);
+        e.dist[4] = uni(r[5].x, P.rd.dist_lo[4], P.rd.dist_span[4]);
+        e.dist[5] = uni(r[5].y, P.rd.dist_lo[5], P.rd.dist_span[5]);
+    } else {
+        e.w[0] = uni(r[3].x, -0.1f, 0.2f);
+    }
+}
+
+// every lane draws for itself (used by reset(), and by the step when many lanes of a warp terminate at once)
 template <int V>
 __device__ __forceinline__ void draw_reset(const StepParams &P, long long env, uint32_t episode, EnvState<V> &e) {
     const unsigned long long g = (unsigned long long)(env + P.env_offset);
-    const uint2 key = make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32));
-    const float pi = 3.14159265358979f, pi9 = 0.349065850398866f;
-    uint4 r0 = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), episode, 0u), key);
-    uint4 r1 = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), episode, 1u), key);
-    uint4 r2 = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), episode, 2u), key);
-    uint4 r3 = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), episode, 3u), key);
-    e.x = P.rd.start[0] + uni(r0.x, -0.5f, 1.0f);
-    e.y = P.rd.start[1] + uni(r0.y, -0.5f, 1.0f);
-    e.z = P.rd.start[2] + uni(r0.z, -0.5f, 1.0f);
-    e.vx = uni(r0.w, -0.5f, 1.0f); e.vy = uni(r1.x, -0.5f, 1.0f); e.vz = uni(r1.y, -0.5f, 1.0f);
-    e.phi = uni(r1.z, -pi9, 2 * pi9); e.th = uni(r1.w, -pi9, 2 * pi9); e.psi = uni(r2.x, -pi, 2 * pi);
-    e.p = uni(r2.y, -0.1f, 0.2f); e.q = uni(r2.z, -0.1f, 0.2f); e.r = uni(r2.w, -0.1f, 0.2f);
-    if (V == kE2E) {
-        e.w[0] = uni(r3.x, -1.f, 2.f); e.w[1] = uni(r3.y, -1.f, 2.f);
-        e.w[2] = uni(r3.z, -1.f, 2.f); e.w[V == kE2E ? 3 : 0] = uni(r3.w, -1.f, 2.f);
-        uint4 r4 = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), episode, 4u), key);
-        uint4 r5 = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), episode, 5u), key);
-        e.dist[0] = uni(r4.x, P.rd.dist_lo[0], P.rd.dist_span[0]);
-        e.dist[1] = uni(r4.y, P.rd.dist_lo[1], P.rd.dist_span[1]);
-        e.dist[2] = uni(r4.z, P.rd.dist_lo[2], P.rd.dist_span[2]);
-        e.dist[3] = uni(r4.w, P.rd.dist_lo[3], P.rd.dist_span[3]);
-        e.dist[4] = uni(r5.x, P.rd.dist_lo[4], P.rd.dist_span[4]);
-        e.dist[5] = uni(r5.y, P.rd.dist_lo[5], P.rd.dist_span[5]);
-    } else {
-        e.w[0] = uni(r3.x, -0.1f, 0.2f);
+    uint4 r[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) r[c] = c < ResetDraws<V>::N ? reset_draw(P, g, episode, c) : make_uint4(0, 0, 0, 0);
+    fill_reset<V>(P, r, e);
+}
+
+// Warp-cooperative form for the common case of one or two terminating lanes per warp: instead of one lane
+// running 6 Philox evaluations while 31 wait, lanes 0..5 each run ONE for that env and hand the words over by
+// shuffle.  Must be called by the whole warp; `need` marks the lanes that reset.  Same values as draw_reset.
+template <int V>
+__device__ __forceinline__ void draw_reset_warp(const StepParams &P, long long env, uint32_t episode, bool need,
+                                                EnvState<V> &e) {
+    const unsigned full = 0xffffffffu;
+    unsigned m = __ballot_sync(full, need);
+    if (m == 0) return;
+    if (__popc(m) > 4) {  // mass termination (e.g. synchronous time-outs): per-lane is cheaper
+        if (need) draw_reset<V>(P, env, episode, e);
+        return;
+    }
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned long long g_own = (unsigned long long)(env + P.env_offset);
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t g_lo = __shfl_sync(full, (uint32_t)g_own, src), g_hi = __shfl_sync(full, (uint32_t)(g_own >> 32), src);
+        const uint32_t ep = __shfl_sync(full, episode, src);
+        const uint4 mine = reset_draw(P, ((unsigned long long)g_hi << 32) | g_lo, ep, lane & 7);
+        uint4 r[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            if (c < ResetDraws<V>::N) {
+                r[c].x = __shfl_sync(full, mine.x, c); r[c].y = __shfl_sync(full, mine.y, c);
+                r[c].z = __shfl_sync(full, mine.z, c); r[c].w = __shfl_sync(full, mine.w, c);
+            } else {
+                r[c] = make_uint4(0, 0, 0, 0);
+            }
+        }
+        if ((int)lane == src) fill_reset<V>(P, r, e);
     }
 }
 
@@ -260,33 +312,98 @@ __device__ __forceinline__ void load_track(const StepParams &P, float *s_track) 
 }
 
 // ------------------------------------------------------------------------------------------------ dynamics
+// packed FP32: one FFMA2 issues two FMAs (Blackwell `fma.rn.f32x2`); operands are 64-bit register pairs,
+// a uniform-register pair straight from the constant bank, or a scalar broadcast to both halves.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 // thrust_moment_model_world_states (`:254-262`): two Linear-ReLU-Linear nets sharing their first 7 inputs.
-// Weights are kernel parameters (constant bank): every FFMA takes its weight as an immediate c[0][..] operand,
-// no load instruction and no register -- cheaper than shared memory for warp-uniform data.
+// Weights are kernel parameters (constant bank, warp-uniform): LDCU.128 brings four of them into uniform
+// registers and each FFMA2 consumes a PAIR of hidden units -- 336 FFMA2 + 168 LDCU.128 for the 672 MACs,
+// measured on B200 at the same FMA/clk as scalar FFMA in half the issue slots (profiles/microbench).
 __device__ __forceinline__ void residual_mlp(const StepParams &P, const float (&x)[10], float &thrust, float (&mom)[3]) {
-    const float *w1 = P.wt, *b1 = P.wt + 224, *w2 = P.wt + 256;
-    float acc = P.wt[288];
+    f32x2 xx[10];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        float h = b1[j];
+    for (int k = 0; k < 10; ++k) xx[k] = pack2(x[k], x[k]);
+    // four hidden units per trip: each LDCU.128 of W1^T feeds two FFMA2
+    f32x2 at = pack2(P.b2[0], 0.0f);
 #pragma unroll
-        for (int k = 0; k < 7; ++k) h = fmaf(x[k], w1[j * 7 + k], h);
-        acc = fmaf(fmaxf(h, 0.0f), w2[j], acc);
+    for (int j = 0; j < 32; j += 4) {
+        f32x2 h01 = pack2(P.bt1[j], P.bt1[j + 1]), h23 = pack2(P.bt1[j + 2], P.bt1[j + 3]);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            h01 = fma2(pack2(P.wt1[k * 32 + j], P.wt1[k * 32 + j + 1]), xx[k], h01);
+            h23 = fma2(pack2(P.wt1[k * 32 + j + 2], P.wt1[k * 32 + j + 3]), xx[k], h23);
+        }
+        float h0, h1, h2, h3;
+        unpack2(h01, h0, h1);
+        unpack2(h23, h2, h3);
+        at = fma2(pack2(fmaxf(h0, 0.0f), fmaxf(h1, 0.0f)), pack2(P.wt2[j], P.wt2[j + 1]), at);
+        at = fma2(pack2(fmaxf(h2, 0.0f), fmaxf(h3, 0.0f)), pack2(P.wt2[j + 2], P.wt2[j + 3]), at);
     }
-    thrust = acc;
-    const float *m1 = P.wm, *c1 = P.wm + 320, *m2 = P.wm + 352;
-    float a0 = P.wm[448], a1 = P.wm[449], a2 = P.wm[450];
+    float lo, hi;
+    unpack2(at, lo, hi);
+    thrust = lo + hi;
+    f32x2 a0 = pack2(P.b2[1], 0.0f), a1 = pack2(P.b2[2], 0.0f), a2 = pack2(P.b2[3], 0.0f);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        float h = c1[j];
+    for (int j = 0; j < 32; j += 4) {
+        f32x2 h01 = pack2(P.bm1[j], P.bm1[j + 1]), h23 = pack2(P.bm1[j + 2], P.bm1[j + 3]);
 #pragma unroll
-        for (int k = 0; k < 10; ++k) h = fmaf(x[k], m1[j * 10 + k], h);
-        h = fmaxf(h, 0.0f);
-        a0 = fmaf(h, m2[j], a0);
-        a1 = fmaf(h, m2[32 + j], a1);
-        a2 = fmaf(h, m2[64 + j], a2);
+        for (int k = 0; k < 10; ++k) {
+            h01 = fma2(pack2(P.wm1[k * 32 + j], P.wm1[k * 32 + j + 1]), xx[k], h01);
+            h23 = fma2(pack2(P.wm1[k * 32 + j + 2], P.wm1[k * 32 + j + 3]), xx[k], h23);
+        }
+        float h0, h1, h2, h3;
+        unpack2(h01, h0, h1);
+        unpack2(h23, h2, h3);
+        const f32x2 r01 = pack2(fmaxf(h0, 0.0f), fmaxf(h1, 0.0f)), r23 = pack2(fmaxf(h2, 0.0f), fmaxf(h3, 0.0f));
+        a0 = fma2(r01, pack2(P.wm2[j], P.wm2[j + 1]), a0);
+        a0 = fma2(r23, pack2(P.wm2[j + 2], P.wm2[j + 3]), a0);
+        a1 = fma2(r01, pack2(P.wm2[32 + j], P.wm2[32 + j + 1]), a1);
+        a1 = fma2(r23, pack2(P.wm2[32 + j + 2], P.wm2[32 + j + 3]), a1);
+        a2 = fma2(r01, pack2(P.wm2[64 + j], P.wm2[64 + j + 1]), a2);
+        a2 = fma2(r23, pack2(P.wm2[64 + j + 2], P.wm2[64 + j + 3]), a2);
     }
-    mom[0] = a0; mom[1] = a1; mom[2] = a2;
+    unpack2(a0, lo, hi); mom[0] = lo + hi;
+    unpack2(a1, lo, hi); mom[1] = lo + hi;
+    unpack2(a2, lo, hi); mom[2] = lo + hi;
+}
+
+// sin and cos together: 3-term Cody-Waite reduction by pi/2 and degree-7/8 minimax polynomials (Cephes
+// coefficients), <= 1.5 ulp on |x| < 1e5 -- the same error class as NumPy's float32 sin/cos (1.45 ulp), see
+// tests/test_kernel_math_models.py.  Huge arguments (a blown-up yaw) take the library's Payne-Hanek path
+// out of line, so the hot code stays small and needs no stack frame.
+__device__ __noinline__ void sincos_slow(float x, float *s, float *c) { sincosf(x, s, c); }
+
+__device__ __forceinline__ void sincos_fast(float x, float &sn, float &cs) {
+    if (fabsf(x) > 1.0e5f) { sincos_slow(x, &sn, &cs); return; }   // also NaN/Inf
+    const float j = rintf(x * 0.636619772367581343f);
+    const int q = (int)j;
+    float a = fmaf(j, -1.5707962512969970703f, x);
+    a = fmaf(j, -7.5497894158615963534e-08f, a);
+    a = fmaf(j, -5.3903029534742383927e-15f, a);
+    const float z = a * a;
+    float ps = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+    ps = fmaf(ps, z, -1.6666654611e-1f);
+    const float s = fmaf(a * z, ps, a);
+    float pc = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    pc = fmaf(pc, z, 4.166664568298827e-2f);
+    pc = fmaf(pc, z, -0.5f);
+    const float c = fmaf(pc, z, 1.0f);
+    const bool swap = q & 1;
+    float ss = swap ? c : s, cc = swap ? s : c;
+    sn = (q & 2) ? -ss : ss;
+    cs = ((q + 1) & 2) ? -cc : cc;
 }
 
 // new = state + dt * f(state, action[, residual + disturbance])  (`:503-512`; INDI `:304`)
@@ -294,9 +411,9 @@ template <int V>
 __device__ __forceinline__ void euler_step(const StepParams &P, const EnvState<V> &e, const float4 u, EnvState<V> &n) {
     const float dt = P.dt;
     float sph, cph, sth, cth, sps, cps;
-    sincosf(e.phi, &sph, &cph);
-    sincosf(e.th, &sth, &cth);
-    sincosf(e.psi, &sps, &cps);
+    sincos_fast(e.phi, sph, cph);
+    sincos_fast(e.th, sth, cth);
+    sincos_fast(e.psi, sps, cps);
     // R = Rz*Ry*Rx
     const float r00 = cps * cth, r10 = sps * cth, r20 = -sth;
     const float r01 = sph * sth * cps - sps * cph, r11 = sph * sps * sth + cph * cps, r21 = sph * cth;
@@ -363,25 +480,141 @@ __device__ __forceinline__ void euler_step(const StepParams &P, const EnvState<V
     n.p = fmaf(dt, dp, e.p); n.q = fmaf(dt, dq, e.q); n.r = fmaf(dt, dr, e.r);
 }
 
-// ------------------------------------------------------------------------------------------------ the step kernel
-template <int V>
-__global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ StepParams P) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *s_obs = reinterpret_cast<float *>(smem_raw);
-    float *s_track = s_obs + kBlock * P.obs_len;
-    load_track(P, s_track);
+// ------------------------------------------------------------------------------------------------ async-proxy primitives
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *dst, const void *src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-    const long long base = (long long)blockIdx.x * kBlock;
-    const long long env = base + threadIdx.x;
-    const bool active = env < P.n;
-    float reward = 0.0f;
-    uint32_t fl = 0;
-    if (active) {
+// ------------------------------------------------------------------------------------------------ the step kernel
+// Input tile of one pipeline stage: the 128 envs of a tile are 2 KB-contiguous in every plane, so a stage is
+// filled by 6-8 bulk copies issued by ONE thread; nobody else spends an instruction on global loads.
+template <int V> struct Stage;
+template <> struct Stage<kE2E> {
+    enum : int { P0 = 0, P1 = 2048, P2 = 4096, P3 = 6144, DA = 8192, DB = 10240, META = 11264, ACT = 11776, BYTES = 13824 };
+};
+template <> struct Stage<kINDI> {
+    enum : int { P0 = 0, P1 = 2048, P2 = 4096, P3 = 6144, META = 6656, ACT = 7168, BYTES = 9216, DA = 0, DB = 0 };
+};
+constexpr int kBarBytes = 128;  // mbarriers live in the first 128 bytes of dynamic shared memory
+
+__host__ __device__ constexpr size_t step_smem_bytes(int variant, int stages, int obs_len, int n_gates) {
+    return kBarBytes + (size_t)stages * (variant == kE2E ? (int)Stage<kE2E>::BYTES : (int)Stage<kINDI>::BYTES) +
+           (size_t)kBlock * obs_len * 4 + (size_t)n_gates * kTrackRow * 4;
+}
+
+template <int V>
+__device__ __forceinline__ void issue_tile(const StepParams &P, unsigned char *st, uint64_t *bar, long long tile) {
+    using S = Stage<V>;
+    const long long base = tile * kBlock;
+    const long long rem = P.n - base;
+    const uint32_t act_bytes = (uint32_t)(rem < kBlock ? rem : kBlock) * 16u;  // caller's buffer is not padded
+    mbar_expect_tx(bar, (uint32_t)S::BYTES - 2048u + act_bytes);
+    bulk_load(st + S::P0, P.s.p0 + base, 2048, bar);
+    bulk_load(st + S::P1, P.s.p1 + base, 2048, bar);
+    bulk_load(st + S::P2, P.s.p2 + base, 2048, bar);
+    if (V == kE2E) {
+        bulk_load(st + S::P3, P.s.p3 + base, 2048, bar);
+        bulk_load(st + S::DA, P.s.da + base, 2048, bar);
+        bulk_load(st + S::DB, P.s.db + base, 1024, bar);
+    } else {
+        bulk_load(st + S::P3, P.s.p3s + base, 512, bar);
+    }
+    bulk_load(st + S::META, P.s.meta + base, 512, bar);
+    bulk_load(st + S::ACT, P.actions + base, act_bytes, bar);
+}
+
+// Persistent CTAs (grid = SMs x resident CTAs), each looping over 128-env tiles through a kStages-deep ring of
+// shared-memory stages: while tile i is being computed, the TMA engine is already filling the stages of the next
+// tiles, so HBM latency never sits on a warp's scoreboard.  Per tile: 1 mbarrier wait, 2 block barriers.
+template <int V, int kStages>
+__global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ StepParams P) {
+    using S = Stage<V>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+    unsigned char *stages = smem_raw + kBarBytes;
+    float *s_obs = reinterpret_cast<float *>(stages + kStages * S::BYTES);
+    float *s_track = s_obs + kBlock * P.obs_len;
+    const int tid = threadIdx.x;
+    const long long n_tiles = (P.n + kBlock - 1) / kBlock;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    load_track(P, s_track);  // ends with __syncthreads(): barrier init is visible to everyone
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
+            if (t < n_tiles) issue_tile<V>(P, stages + s * S::BYTES, &full[s], t);
+        }
+    }
+
+    float reward_acc = 0.0f;  // stats are reduced once per CTA lifetime, not per tile
+    unsigned c_act = 0, c_done = 0, c_tr = 0, c_gp = 0, c_gc = 0, c_gr = 0, c_ob = 0;
+    const bool write_obs_tile = P.mode != kModePause;
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int stage = it % kStages;
+        unsigned char *st = stages + stage * S::BYTES;
+        const long long base = tile * kBlock;
+        const long long env = base + tid;
+        const bool active = env < P.n;
+        mbar_wait(&full[stage], (uint32_t)(it / kStages) & 1u);
+
+        // ---- stage -> registers (conflict-free: consecutive threads read consecutive 16-byte words)
         EnvState<V> e, n;
-        load_state<V>(P.s, env, e);
-        const float4 u = P.actions[env];
-        const uint32_t meta = P.s.meta[env];
+        {
+            const float4 a = reinterpret_cast<const float4 *>(st + S::P0)[tid];
+            const float4 b = reinterpret_cast<const float4 *>(st + S::P1)[tid];
+            const float4 c = reinterpret_cast<const float4 *>(st + S::P2)[tid];
+            e.x = a.x; e.y = a.y; e.z = a.z; e.vx = a.w; e.vy = b.x; e.vz = b.y; e.phi = b.z; e.th = b.w;
+            e.psi = c.x; e.p = c.y; e.q = c.z; e.r = c.w;
+            if (V == kE2E) {
+                const float4 d = reinterpret_cast<const float4 *>(st + S::P3)[tid];
+                const float4 da = reinterpret_cast<const float4 *>(st + S::DA)[tid];
+                const float2 db = reinterpret_cast<const float2 *>(st + S::DB)[tid];
+                e.w[0] = d.x; e.w[1] = d.y; e.w[2] = d.z; e.w[V == kE2E ? 3 : 0] = d.w;
+                e.dist[0] = da.x; e.dist[1] = da.y; e.dist[2] = da.z; e.dist[5] = da.w; e.dist[3] = db.x; e.dist[4] = db.y;
+            } else {
+                e.w[0] = reinterpret_cast<const float *>(st + S::P3)[tid];
+            }
+        }
+        const float4 u = reinterpret_cast<const float4 *>(st + S::ACT)[tid];
+        const uint32_t meta = reinterpret_cast<const uint32_t *>(st + S::META)[tid];
         uint32_t tg = meta >> 24, sc = meta & kStepMask;
+        if (tid == 0 && it > 0 && write_obs_tile) bulk_store_wait_read();  // previous tile's obs has left s_obs
+        __syncthreads();  // [A] every thread holds its inputs: the stage and s_obs may be overwritten
+        if (tid == 0) {
+            const long long nt = tile + (long long)kStages * gridDim.x;
+            if (nt < n_tiles) issue_tile<V>(P, st, &full[stage], nt);
+        }
 
         euler_step<V>(P, e, u, n);
         sc = sc < kStepMask ? sc + 1 : sc;  // step_counts += 1 (`:514`), saturating in 24 bits
@@ -392,7 +625,7 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ St
         const float ox = sub_rn(e.x, ga.x), oy = sub_rn(e.y, ga.y), oz = sub_rn(e.z, ga.z);
         const float nx = sub_rn(n.x, ga.x), ny = sub_rn(n.y, ga.y), nz = sub_rn(n.z, ga.z);
         const float d_old = norm3_rn(ox, oy, oz), d_new = norm3_rn(nx, ny, nz);
-        reward = sub_rn(d_old, d_new);
+        float reward = sub_rn(d_old, d_new);
         const float proj_old = add_rn(mul_rn(ox, gcs.x), mul_rn(oy, gcs.y));
         const float proj_new = add_rn(mul_rn(nx, gcs.x), mul_rn(ny, gcs.y));
         const bool plane = (proj_old < 0.0f) && (proj_new > 0.0f);
@@ -407,57 +640,78 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ St
         if (collided | ground | oob) reward = -10.0f;
         if (passed) tg = (tg + 1 == (uint32_t)P.n_gates) ? 0u : tg + 1;  // (`:556-557`)
         const bool dn = trunc | ground | collided | oob;
-        fl = (dn ? F_DONE : 0u) | (trunc ? F_TRUNC : 0u) | (passed ? F_PASSED : 0u) | (collided ? F_COLLISION : 0u) |
-             (ground ? F_GROUND : 0u) | (oob ? F_OOB : 0u);
+        const uint32_t fl = (dn ? F_DONE : 0u) | (trunc ? F_TRUNC : 0u) | (passed ? F_PASSED : 0u) |
+                            (collided ? F_COLLISION : 0u) | (ground ? F_GROUND : 0u) | (oob ? F_OOB : 0u);
 
         // ---- branch logic (`:568-585`)
-        bool write_world = true, write_dist = false;
+        bool write_world = active, write_dist = false;
         if (P.mode == kModeNormal) {
-            if (dn && P.reset_source == kResetDevice) {
-                const uint32_t ep = P.s.episode[env];
-                draw_reset<V>(P, env, ep, n);
-                P.s.episode[env] = ep + 1;
-                tg = 0; sc = 0;
-                write_dist = (V == kE2E);
+            if (P.reset_source == kResetDevice) {  // block-uniform branch: the whole warp takes part in the draw
+                const bool need = dn && active;
+                uint32_t ep = 0;
+                if (need) ep = P.s.episode[env];
+                draw_reset_warp<V>(P, env, ep, need, n);
+                if (need) {
+                    P.s.episode[env] = ep + 1;
+                    tg = 0; sc = 0;
+                    write_dist = (V == kE2E);
+                }
             }
         } else if (P.mode == kModePauseIfCollision) {
             if (dn) { n = e; write_world = false; }
         } else {  // env.pause
             write_world = false;
         }
-        P.s.meta[env] = (tg << 24) | sc;
+        if (active) {
+            P.s.meta[env] = (tg << 24) | sc;
+            P.rew[env] = reward;
+            P.done[env] = (P.mode == kModePause) ? (uint8_t)0 : (uint8_t)(dn ? 1 : 0);
+            if (P.flags) P.flags[env] = (uint8_t)fl;
+        }
         if (write_world) store_world<V>(P.s, env, n);
         if (write_dist) store_dist<V>(P.s, env, n);
-        P.rew[env] = reward;
-        P.done[env] = (P.mode == kModePause) ? (uint8_t)0 : (uint8_t)(dn ? 1 : 0);
-        if (P.flags) P.flags[env] = (uint8_t)fl;
-        if (P.mode != kModePause) write_obs<V>(P, s_track, n, tg, s_obs + threadIdx.x * P.obs_len);
+
+        if (write_obs_tile) {
+            write_obs<V>(P, s_track, n, tg, s_obs + tid * P.obs_len);
+            const long long rem = P.n - base;
+            const int rows = rem < kBlock ? (int)rem : kBlock;
+            float *dst = P.obs + base * P.obs_len;
+            const uint32_t bytes = (uint32_t)rows * (uint32_t)P.obs_len * 4u;
+            const bool bulk = ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) && ((bytes & 15u) == 0);
+            if (bulk) {  // the tile's rows are contiguous in the (N,D) output: one TMA bulk store
+                fence_proxy_async();
+                __syncthreads();  // [B]
+                if (tid == 0) bulk_store(dst, s_obs, bytes);
+            } else {
+                __syncthreads();
+                for (int i = tid; i < rows * P.obs_len; i += kBlock) dst[i] = s_obs[i];
+            }
+        }
+        if (P.stats && active) {
+            reward_acc += reward;
+            c_act += 1; c_done += (fl & F_DONE) != 0; c_tr += (fl & F_TRUNC) != 0; c_gp += (fl & F_PASSED) != 0;
+            c_gc += (fl & F_COLLISION) != 0; c_gr += (fl & F_GROUND) != 0; c_ob += (fl & F_OOB) != 0;
+        }
     }
-    if (P.mode != kModePause) {
-        const long long rem = P.n - base;
-        store_obs_tile(P.obs + base * P.obs_len, s_obs, rem < kBlock ? (int)rem : kBlock, P.obs_len);
-    }
+    if (tid == 0 && write_obs_tile) bulk_store_wait_read();  // shared memory must outlive the last bulk read
+
     if (P.stats) {  // warp-level reduction of the reward and the flag counters, one atomic set per warp
-        const unsigned full = 0xffffffffu;
-        float rs = reward;
+        const unsigned full_mask = 0xffffffffu;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(full, rs, o);
-        const unsigned n_act = __popc(__ballot_sync(full, active));
-        const unsigned n_done = __popc(__ballot_sync(full, fl & F_DONE));
-        const unsigned n_tr = __popc(__ballot_sync(full, fl & F_TRUNC));
-        const unsigned n_gp = __popc(__ballot_sync(full, fl & F_PASSED));
-        const unsigned n_gc = __popc(__ballot_sync(full, fl & F_COLLISION));
-        const unsigned n_gr = __popc(__ballot_sync(full, fl & F_GROUND));
-        const unsigned n_ob = __popc(__ballot_sync(full, fl & F_OOB));
-        if ((threadIdx.x & 31) == 0 && n_act) {
-            atomicAdd(&P.stats->reward_sum, (double)rs);
-            atomicAdd(&P.stats->env_steps, (unsigned long long)n_act);
-            if (n_done) atomicAdd(&P.stats->dones, (unsigned long long)n_done);
-            if (n_tr) atomicAdd(&P.stats->truncated, (unsigned long long)n_tr);
-            if (n_gp) atomicAdd(&P.stats->gates_passed, (unsigned long long)n_gp);
-            if (n_gc) atomicAdd(&P.stats->gate_collisions, (unsigned long long)n_gc);
-            if (n_gr) atomicAdd(&P.stats->ground_collisions, (unsigned long long)n_gr);
-            if (n_ob) atomicAdd(&P.stats->out_of_bounds, (unsigned long long)n_ob);
+        for (int o = 16; o > 0; o >>= 1) reward_acc += __shfl_xor_sync(full_mask, reward_acc, o);
+        c_act = __reduce_add_sync(full_mask, c_act); c_done = __reduce_add_sync(full_mask, c_done);
+        c_tr = __reduce_add_sync(full_mask, c_tr); c_gp = __reduce_add_sync(full_mask, c_gp);
+        c_gc = __reduce_add_sync(full_mask, c_gc); c_gr = __reduce_add_sync(full_mask, c_gr);
+        c_ob = __reduce_add_sync(full_mask, c_ob);
+        if ((tid & 31) == 0 && c_act) {
+            atomicAdd(&P.stats->reward_sum, (double)reward_acc);
+            atomicAdd(&P.stats->env_steps, (unsigned long long)c_act);
+            if (c_done) atomicAdd(&P.stats->dones, (unsigned long long)c_done);
+            if (c_tr) atomicAdd(&P.stats->truncated, (unsigned long long)c_tr);
+            if (c_gp) atomicAdd(&P.stats->gates_passed, (unsigned long long)c_gp);
+            if (c_gc) atomicAdd(&P.stats->gate_collisions, (unsigned long long)c_gc);
+            if (c_gr) atomicAdd(&P.stats->ground_collisions, (unsigned long long)c_gr);
+            if (c_ob) atomicAdd(&P.stats->out_of_bounds, (unsigned long long)c_ob);
         }
     }
 }
