@@ -36,8 +36,12 @@ class ObsAllGather:
             return self.buf
         if self.equal:
             dist.all_gather_into_tensor(self.buf, self.local_slot(), group=self.group)
-        else:  # ragged shards: list form
-            outs = [self.buf[f:f + c] for f, c in (shard_range(self.buf.shape[0], r, self.world)
-                                                    for r in range(self.world))]
-            dist.all_gather(outs, self.local_slot().contiguous(), group=self.group)
+        else:  # ragged shards (total_envs % world != 0): every rank broadcasts its block in place
+            works = []
+            for r in range(self.world):
+                f, c = shard_range(self.buf.shape[0], r, self.world)
+                src = dist.get_global_rank(self.group, r) if self.group is not None else r
+                works.append(dist.broadcast(self.buf[f:f + c], src=src, group=self.group, async_op=True))
+            for w in works:
+                w.wait()
         return self.buf

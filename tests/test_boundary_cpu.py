@@ -1,0 +1,149 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads and exports every symbol include/quadsim.h
+declares (no compute calls -- there is no GPU here), argument errors come back as status codes, the product
+package never reaches into oracle/, and the N>1 sharding logic works under a world_size-2 gloo group."""
+import ctypes as C
+import os
+import re
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "quadsim.h")
+PKG = os.path.join(ROOT, "optimal_quad_control_rl_b200")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(qs_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_table_agree():
+    from optimal_quad_control_rl_b200 import _lib as L
+    assert set(declared_symbols()) == set(L.SIGNATURES), set(declared_symbols()) ^ set(L.SIGNATURES)
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from optimal_quad_control_rl_b200 import _lib as L
+    lib = L.load()  # builds with nvcc (cross-compile) when missing or stale
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.qs_version()
+    # pure host-side entry points are callable without a device
+    assert lib.qs_state_len(L.E2E) == 16 and lib.qs_state_len(L.INDI) == 13
+    assert lib.qs_obs_len(L.E2E, 1) == 24 and lib.qs_obs_len(L.INDI, 1) == 17
+    assert lib.qs_algorithmic_bytes_per_env_step(L.E2E, 1) == 285
+    assert lib.qs_algorithmic_bytes_per_env_step(L.INDI, 1) == 209
+
+
+def test_library_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", os.path.join(PKG, "libquadsim.so")], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_\d+a?", out.stdout))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_argument_errors_are_status_codes_not_crashes():
+    from optimal_quad_control_rl_b200 import _lib as L
+    lib = L.load()
+    h = L._vp()
+    gp = np.zeros((2, 3), np.float32)
+    gy = np.zeros(2, np.float32)
+    sp = np.zeros(3, np.float32)
+    f = lambda a: a.ctypes.data_as(L._fp)
+    assert lib.qs_create(C.byref(h), 7, 16, 2, f(gp), f(gy), f(sp), 1, 0, None) == -1  # unknown variant
+    assert b"variant" in lib.qs_last_error(None)
+    assert lib.qs_create(C.byref(h), L.E2E, 0, 2, f(gp), f(gy), f(sp), 1, 0, None) == -1  # num_envs
+    assert lib.qs_create(C.byref(h), L.E2E, 16, 0, f(gp), f(gy), f(sp), 1, 0, None) == -1  # n_gates
+    assert lib.qs_create(C.byref(h), L.E2E, 16, 2, None, f(gy), f(sp), 1, 0, None) == -1  # NULL track
+    assert not h.value
+    assert lib.qs_step(None, None, None, None, None, None, 0, 0) == -1
+    assert lib.qs_destroy(None) == 0
+
+
+def test_env_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import optimal_quad_control_rl_b200 as Q
+    from optimal_quad_control_rl_b200._lib import QuadsimError
+    gp, gy, sp = Q.zigzag_track()
+    with pytest.raises(QuadsimError):
+        Q.Quadcopter3DGates(4, gp, gy, sp, gates_ahead=1)
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(PKG):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), fn
+                assert "quadsim_oracle" not in text, fn
+
+
+def test_tracks_match_golden():
+    import optimal_quad_control_rl_b200 as Q
+    from conftest import golden
+    k = golden("kat")
+    for v, t in (("e2e", Q.zigzag_track()), ("indi", Q.rectangle_track())):
+        np.testing.assert_array_equal(np.asarray(t[0], np.float32), k[f"{v}_gate_pos"])
+        np.testing.assert_array_equal(np.asarray(t[1], np.float32), k[f"{v}_gate_yaw"])
+        np.testing.assert_array_equal(np.asarray(t[2], np.float32), k[f"{v}_start_pos"])
+
+
+def test_shard_range_partitions_exactly():
+    from optimal_quad_control_rl_b200 import shard_range
+    for total in (1, 7, 4096, (1 << 20) + 3):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and sum(c for _, c in spans) == total
+            for (f0, c0), (f1, _) in zip(spans, spans[1:]):
+                assert f0 + c0 == f1
+            assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+from optimal_quad_control_rl_b200 import ObsAllGather, shard_range
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+for total in (64, 67):                       # equal and ragged shards
+    g = ObsAllGather(total, 24, "cpu")
+    first, count = shard_range(total, rank, world)
+    assert (g.first, g.count) == (first, count)
+    slot = g.local_slot()                    # the step kernel writes here (a view of the gather buffer)
+    assert slot.data_ptr() == g.buf[first:].data_ptr()
+    slot.copy_(torch.arange(first, first + count, dtype=torch.float32)[:, None].expand(count, 24))
+    out = g.gather()
+    want = torch.arange(total, dtype=torch.float32)[:, None].expand(total, 24)
+    assert torch.equal(out, want), (rank, total)
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_obs_all_gather_world_size_2_gloo(tmp_path):
+    """The N>1 path on CPU: two gloo ranks, each owning a contiguous block of envs, one all-gather of observations."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for r, p in enumerate(procs):
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out
+        assert f"ok {r}" in out
