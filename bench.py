@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather-obs", action="store_true", help="add the NCCL all-gather of observations per step")
+    ap.add_argument("--no-stats", action="store_true", help="do not accumulate the device-side reward/flag totals")
+    ap.add_argument("--graph", type=int, default=20,
+                    help="replay the timed steps as a CUDA graph of this many steps (0 = one launch call per step)")
     return ap.parse_args()
 
 
@@ -194,7 +197,7 @@ def run_ours(a):
               obs_buffers=2)
     if a.variant == "e2e":
         env.disturbance_ranges = Q.training_disturbance_ranges()
-    env.enable_stats(True)
+    env.enable_stats(not a.no_stats)
     env.reset_tensor()
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
     acts = [torch.rand((n, 4), generator=gen, device=dev) * 2 - 1 for _ in range(4)]  # resident, > L2 with obs
@@ -215,6 +218,26 @@ def run_ours(a):
     W, K = max(a.warmup, 3), a.steps
     for i in range(W):
         one_step(i)
+    graph = None
+    if gather is not None:
+        a.graph = 0  # the collective is issued by torch.distributed per step
+    if a.graph > 0:  # launch-bound regime: capture `graph` consecutive steps once, replay K/graph times
+        g = a.graph - a.graph % 4  # whole action-buffer cycles, and a divisor of K
+        while g >= 4 and K % g:
+            g -= 4
+        a.graph = g if g >= 4 else 0
+    if a.graph > 0:
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            one_step(0)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(a.graph):
+                one_step(i)
+        for _ in range(2):
+            graph.replay()
     env.stats(reset=True)
     l0 = env.launch_count
     sampler = ClockSampler(local)
@@ -222,13 +245,17 @@ def run_ours(a):
     barrier()
     sampler.start()
     e0.record()
-    for i in range(K):
-        one_step(i)
+    if graph is None:
+        for i in range(K):
+            one_step(i)
+    else:
+        for _ in range(K // a.graph):
+            graph.replay()
     e1.record()
     barrier()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
-    launches = env.launch_count - l0
+    launches = env.launch_count - l0 if graph is None else K  # graph replays launch the same kernels
     st = env.stats(reset=True)
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -291,7 +318,8 @@ def run_ours(a):
                        f"{n * (bpe + 16 * 3) / 1e6:.0f} MB touched per step vs 126 MB L2, no flush",
                        "parallelism": f"env-sharded x{world}, no data-path collective" +
                                       (" + NCCL obs all-gather" if gather is not None else ""),
-                       "done_rate": st["dones"] / max(1, st["env_steps"])},
+                       "done_rate": st["dones"] / max(1, st["env_steps"]) if not a.no_stats else None,
+                       "launch": "cuda-graph x%d" % a.graph if graph is not None else "per-step"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "bytes_per_env_step": bpe,
                          "kernel": f"qs::step_kernel<{a.variant}>", "kernel_ms": kernel_ms},

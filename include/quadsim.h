@@ -14,7 +14,7 @@
  *   - a handle is not thread-safe.  One process per GPU; a shard of a larger job sets qs_set_env_offset so that
  *     the device RNG is keyed by the GLOBAL env index and results do not depend on the number of GPUs.
  *
- * State lives on the device as a struct-of-arrays of float4 planes (see DESIGN.md "Data layout"); the
+ * State lives on the device as 32-env blocks of float4 planes (array of structs of arrays, DESIGN.md "Data layout"); the
  * reference's array-of-structs views (`world_states (N,16|13)`, `disturbances (N,6)`, `target_gates`,
  * `step_counts`) are produced on demand by qs_get_state / consumed by qs_set_state.
  */
@@ -50,7 +50,7 @@ typedef enum {
 
 /* who provides the reset draws of reset_ (`:452-493`) in QS_MODE_NORMAL */
 typedef enum {
-    QS_RESET_DEVICE = 0, /* fused in the step kernel: Philox4x32-10 keyed by (seed, global env, episode) -- fast path */
+    QS_RESET_DEVICE = 0, /* fused in the step kernel: Philox4x32-10 keyed by (seed, global env, launch epoch) -- fast path */
     QS_RESET_HOST = 1    /* step leaves done envs un-reset; the host draws (np.random, reference order) and calls
                             qs_apply_reset -- bit-for-bit the reference's reset values */
 } qs_reset_source;
@@ -109,7 +109,7 @@ int qs_set_dt(qs_env *env, float dt);                               /* env.dt (d
 int qs_set_disturbance_ranges(qs_env *env, const double *ranges12, int ranges_are_f64, double scale);
 /* thrust_model.pt / moment_model.pt parameters, row-major [out][in] as torch stores them (`:228-245`) */
 int qs_set_residual_weights(qs_env *env, const float *thrust289, const float *moment451);
-int qs_seed(qs_env *env, uint64_t seed);                            /* device RNG only                           */
+int qs_seed(qs_env *env, uint64_t seed);                            /* device RNG only; rewinds its launch epoch */
 int qs_set_env_offset(qs_env *env, int64_t global_index_of_env0);   /* shard of a multi-GPU job                  */
 int qs_enable_stats(qs_env *env, int on);
 int qs_get_stats(qs_env *env, qs_stats *out, int reset_after_read); /* synchronises                              */
@@ -159,10 +159,12 @@ void qs_host_free(void *p);
 int qs_algorithmic_bytes_per_env_step(int variant, int gates_ahead);
 /* number of kernel launches issued by this handle so far (bench.py's gpu_launches) */
 uint64_t qs_launch_count(const qs_env *env);
-/* device pointers of the internal planes, for zero-copy consumers: plane 0..3 = world state float4 planes,
- * 4 = disturbances (Mx,My,Mz,Fz) float4, 5 = disturbances (Fx,Fy) float2, 6 = packed counters u32
- * (target_gate<<24 | step_count), 7 = episode counter u32 */
-int qs_get_plane_ptr(qs_env *env, int plane, void **dev_ptr);
+/* geometry of the device-resident state, for zero-copy consumers.  Env i lives in block i/32 at lane i%32; block b
+ * starts at base + b*block_bytes; inside a block every field is a 32-lane plane at offsets7[k]:
+ *   0: (x,y,z,vx) float4   1: (vy,vz,phi,theta) float4   2: (psi,p,q,r) float4   3: (w1..w4) float4 | INDI: T_norm float
+ *   4: packed counters u32 (target_gate<<24 | step_count)   5: disturbances (Mx,My,Mz,Fz) float4   6: (Fx,Fy) float2
+ * (5, 6 are -1 for INDI).  Any out pointer may be NULL. */
+int qs_get_state_layout(qs_env *env, void **base, int *block_bytes, int *offsets7);
 
 #ifdef __cplusplus
 }

@@ -58,7 +58,7 @@ SIGNATURES = {
     "qs_host_free": (None, [_vp]),
     "qs_algorithmic_bytes_per_env_step": (C.c_int, [C.c_int, C.c_int]),
     "qs_launch_count": (C.c_uint64, [_vp]),
-    "qs_get_plane_ptr": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
+    "qs_get_state_layout": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
 }
 
 _LIB = None
@@ -73,8 +73,8 @@ def load(build_if_missing=True):
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
-    if build_if_missing and _build.is_stale():
+    path = os.environ.get("QS_LIB") or _build.LIB  # QS_LIB: an experimental build of the same sources (tools/)
+    if path == _build.LIB and build_if_missing and _build.is_stale():
         try:
             _build.build_library()
         except Exception as exc:  # stale-but-present library is still usable; missing one is fatal

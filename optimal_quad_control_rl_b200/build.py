@@ -31,11 +31,13 @@ def is_stale():
     return any(os.path.getmtime(f) > t for f in SOURCES + HEADERS)
 
 
-def build_library(force=False, verbose=False):
-    """Compile if missing or older than its sources; returns the path of the shared library."""
-    if not force and not is_stale():
+def build_library(force=False, verbose=False, out=None, extra_flags=()):
+    """Compile if missing or older than its sources; returns the path of the shared library.
+    ``out`` / ``extra_flags`` build an experimental variant (e.g. -DQS_EXP_NOMLP) next to the product library."""
+    if out is None and not force and not is_stale():
         return LIB
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", LIB, *SOURCES]
+    out = out or LIB
+    cmd = [nvcc_path(), *NVCC_FLAGS, *extra_flags, "-o", out, *SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -43,7 +45,7 @@ def build_library(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -20,7 +20,7 @@ static_assert(sizeof(qs::Stats) == sizeof(qs_stats), "qs_stats layout");
 static_assert(sizeof(StepParams) < 32000, "kernel parameter block too large");
 
 struct qs_env {
-    int variant = 0, device = 0, n_gates = 0, gates_ahead = 0, obs_len = 0, state_len = 0;
+    int variant = 0, device = 0, n_gates = 0, gates_ahead = 0, obs_len = 0, state_len = 0, block_bytes = 0;
     int64_t n = 0;
     cudaStream_t stream = nullptr;
     Planes planes{};
@@ -35,6 +35,7 @@ struct qs_env {
     int64_t max_steps = 1200;
     float dt = 0.01f;
     uint64_t seed = 0;
+    unsigned long long *epoch_dev = nullptr;  // [0] launches that may draw resets so far (device RNG key), [1] CTA arrivals
     int64_t env_offset = 0;
     StepParams P{};  // weights live here
     // staging for the host-buffer entry points
@@ -44,6 +45,7 @@ struct qs_env {
     size_t scratch_bytes = 0;
     uint64_t launches = 0;
     int stages = 2, step_grid = 0;  // pipeline depth and persistent grid of the step kernel
+    bool pdl = true;                // programmatic dependent launch of consecutive steps
     size_t step_smem = 0;
     std::string err;
 };
@@ -118,6 +120,7 @@ static void refresh_params(qs_env *e) {
     P.n = e->n;
     P.env_offset = e->env_offset;
     P.seed = e->seed;
+    P.epoch = e->epoch_dev;
     P.n_gates = e->n_gates;
     P.gates_ahead = e->gates_ahead;
     P.obs_len = e->obs_len;
@@ -185,28 +188,16 @@ int qs_create(qs_env **out, int variant, int64_t num_envs, int n_gates, const fl
     };
     cudaError_t c;
     if ((c = cudaSetDevice(device)) != cudaSuccess) return bail(c, "cudaSetDevice");
-    // planes are padded to whole 128-env tiles (zero-filled) so that every bulk load of the step kernel is full-size
+    // state: one AoSoA block per 32 envs, padded (zero-filled) to whole 128-env tiles so that every bulk load of
+    // the step kernel is full-size
     const size_t n = ((size_t)num_envs + qs::kBlock - 1) / qs::kBlock * qs::kBlock;
+    e->block_bytes = variant == QS_E2E ? (int)qs::Blk<qs::kE2E>::BYTES : (int)qs::Blk<qs::kINDI>::BYTES;
     Planes &s = e->planes;
-    if ((c = cudaMalloc(&s.p0, n * 16)) != cudaSuccess) return bail(c, "cudaMalloc");
-    if ((c = cudaMalloc(&s.p1, n * 16)) != cudaSuccess) return bail(c, "cudaMalloc");
-    if ((c = cudaMalloc(&s.p2, n * 16)) != cudaSuccess) return bail(c, "cudaMalloc");
-    if (variant == QS_E2E) {
-        if ((c = cudaMalloc(&s.p3, n * 16)) != cudaSuccess) return bail(c, "cudaMalloc");
-        if ((c = cudaMalloc(&s.da, n * 16)) != cudaSuccess) return bail(c, "cudaMalloc");
-        if ((c = cudaMalloc(&s.db, n * 8)) != cudaSuccess) return bail(c, "cudaMalloc");
-        cudaMemset(s.p3, 0, n * 16); cudaMemset(s.da, 0, n * 16); cudaMemset(s.db, 0, n * 8);
-    } else {
-        if ((c = cudaMalloc(&s.p3s, n * 4)) != cudaSuccess) return bail(c, "cudaMalloc");
-        cudaMemset(s.p3s, 0, n * 4);
-    }
-    if ((c = cudaMalloc(&s.meta, n * 4)) != cudaSuccess) return bail(c, "cudaMalloc");
-    if ((c = cudaMalloc(&s.episode, n * 4)) != cudaSuccess) return bail(c, "cudaMalloc");
-    cudaMemset(s.p0, 0, n * 16); cudaMemset(s.p1, 0, n * 16); cudaMemset(s.p2, 0, n * 16);
-    cudaMemset(s.meta, 0, n * 4); cudaMemset(s.episode, 0, n * 4);
+    if ((c = cudaMalloc(&s.base, n / 32 * e->block_bytes)) != cudaSuccess) return bail(c, "cudaMalloc");
+    cudaMemset(s.base, 0, n / 32 * e->block_bytes);
+    if ((c = cudaMalloc(&e->epoch_dev, 16)) != cudaSuccess) return bail(c, "cudaMalloc");
+    cudaMemset(e->epoch_dev, 0, 16);
     if ((c = cudaMalloc(&e->track_dev, (size_t)n_gates * qs::kTrackRow * 4)) != cudaSuccess) return bail(c, "cudaMalloc");
-    if ((c = cudaMalloc(&e->stats_dev, sizeof(qs::Stats))) != cudaSuccess) return bail(c, "cudaMalloc");
-    cudaMemset(e->stats_dev, 0, sizeof(qs::Stats));
     if ((c = cudaDeviceSynchronize()) != cudaSuccess) return bail(c, "cudaDeviceSynchronize");
     // the observation tile + track table must fit in dynamic shared memory
     const size_t smem = smem_bytes(e);
@@ -219,12 +210,13 @@ int qs_create(qs_env **out, int variant, int64_t num_envs, int n_gates, const fl
     }
     // persistent step kernel: pipeline depth, shared memory, grid = SMs x resident CTAs
     if (const char *sv = getenv("QS_STAGES")) e->stages = atoi(sv) == 3 ? 3 : (atoi(sv) == 4 ? 4 : 2);
+    if (const char *pv = getenv("QS_PDL")) e->pdl = atoi(pv) != 0;
     const void *step_fn = step_function(e);
     e->step_smem = qs::step_smem_bytes(variant, e->stages, e->obs_len, n_gates);
     if ((c = cudaFuncSetAttribute(step_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem)) != cudaSuccess)
         return bail(c, "cudaFuncSetAttribute(step smem)");
     int per_sm = 0, sms = 0;
-    if ((c = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_fn, qs::kBlock, e->step_smem)) != cudaSuccess)
+    if ((c = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_fn, qs::kStepThreads, e->step_smem)) != cudaSuccess)
         return bail(c, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
     if ((c = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
         return bail(c, "cudaDeviceGetAttribute");
@@ -232,6 +224,9 @@ int qs_create(qs_env **out, int variant, int64_t num_envs, int n_gates, const fl
     if (const char *cv = getenv("QS_CTAS_PER_SM")) { int v = atoi(cv); if (v >= 1 && v < per_sm) per_sm = v; }
     const long long tiles = (num_envs + qs::kBlock - 1) / qs::kBlock;
     e->step_grid = (int)(tiles < (long long)sms * per_sm ? tiles : (long long)sms * per_sm);
+    // device-side totals: one slot per CTA, updated without atomics, summed on read
+    if ((c = cudaMalloc(&e->stats_dev, sizeof(qs::Stats) * e->step_grid)) != cudaSuccess) return bail(c, "cudaMalloc");
+    if ((c = cudaMemset(e->stats_dev, 0, sizeof(qs::Stats) * e->step_grid)) != cudaSuccess) return bail(c, "cudaMemset");
     *out = e;
     return QS_OK;
 }
@@ -241,8 +236,7 @@ int qs_destroy(qs_env *e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream); else cudaDeviceSynchronize();
     Planes &s = e->planes;
-    cudaFree(s.p0); cudaFree(s.p1); cudaFree(s.p2); cudaFree(s.p3); cudaFree(s.p3s); cudaFree(s.da); cudaFree(s.db);
-    cudaFree(s.meta); cudaFree(s.episode); cudaFree(e->track_dev); cudaFree(e->stats_dev); cudaFree(e->scratch);
+    cudaFree(s.base); cudaFree(e->epoch_dev); cudaFree(e->track_dev); cudaFree(e->stats_dev); cudaFree(e->scratch);
     cudaFree(e->h_act); cudaFree(e->h_obs); cudaFree(e->h_rew); cudaFree(e->h_done); cudaFree(e->h_flags);
     delete e;
     return QS_OK;
@@ -273,7 +267,13 @@ int qs_get_track_tables(qs_env *e, float *gc, float *gs, float *pr, float *yr) {
 
 int qs_set_max_steps(qs_env *e, int64_t m) { QS_CHECK_ENV(e); e->max_steps = m; return QS_OK; }
 int qs_set_dt(qs_env *e, float dt) { QS_CHECK_ENV(e); e->dt = dt; return QS_OK; }
-int qs_seed(qs_env *e, uint64_t seed) { QS_CHECK_ENV(e); e->seed = seed; return QS_OK; }
+int qs_seed(qs_env *e, uint64_t seed) {  // also rewinds the launch epoch: same seed, same calls => same draws
+    QS_CHECK_ENV(e);
+    e->seed = seed;
+    QS_CUDA(e, cudaSetDevice(e->device));
+    QS_CUDA(e, cudaMemsetAsync(e->epoch_dev, 0, 16, e->stream));
+    return QS_OK;
+}
 int qs_set_env_offset(qs_env *e, int64_t off) { QS_CHECK_ENV(e); e->env_offset = off; return QS_OK; }
 
 int qs_set_disturbance_ranges(qs_env *e, const double *r, int is_f64, double scale) {
@@ -311,19 +311,31 @@ int qs_get_stats(qs_env *e, qs_stats *out, int reset) {
     QS_CHECK_ENV(e);
     if (!out) return fail(e, QS_ERR_ARG, "qs_get_stats: NULL");
     QS_CUDA(e, cudaSetDevice(e->device));
-    QS_CUDA(e, cudaMemcpyAsync(out, e->stats_dev, sizeof(qs_stats), cudaMemcpyDeviceToHost, e->stream));
-    if (reset) QS_CUDA(e, cudaMemsetAsync(e->stats_dev, 0, sizeof(qs_stats), e->stream));
+    std::vector<qs_stats> slots((size_t)e->step_grid);
+    const size_t bytes = sizeof(qs_stats) * slots.size();
+    QS_CUDA(e, cudaMemcpyAsync(slots.data(), e->stats_dev, bytes, cudaMemcpyDeviceToHost, e->stream));
+    if (reset) QS_CUDA(e, cudaMemsetAsync(e->stats_dev, 0, bytes, e->stream));
     QS_CUDA(e, cudaStreamSynchronize(e->stream));
+    qs_stats t{};
+    for (const qs_stats &s : slots) {
+        t.reward_sum += s.reward_sum; t.env_steps += s.env_steps; t.dones += s.dones; t.truncated += s.truncated;
+        t.gates_passed += s.gates_passed; t.gate_collisions += s.gate_collisions;
+        t.ground_collisions += s.ground_collisions; t.out_of_bounds += s.out_of_bounds;
+    }
+    *out = t;
     return QS_OK;
 }
 
-int qs_get_plane_ptr(qs_env *e, int plane, void **p) {
+int qs_get_state_layout(qs_env *e, void **base, int *block_bytes, int *offsets7) {
     QS_CHECK_ENV(e);
-    if (!p) return fail(e, QS_ERR_ARG, "qs_get_plane_ptr: NULL");
-    const Planes &s = e->planes;
-    void *tab[8] = {s.p0, s.p1, s.p2, e->variant == QS_E2E ? (void *)s.p3 : (void *)s.p3s, s.da, s.db, s.meta, s.episode};
-    if (plane < 0 || plane > 7) return fail(e, QS_ERR_ARG, "qs_get_plane_ptr: plane must be 0..7");
-    *p = tab[plane];
+    if (base) *base = e->planes.base;
+    if (block_bytes) *block_bytes = e->block_bytes;
+    if (offsets7) {
+        using E = qs::Blk<qs::kE2E>;
+        using I = qs::Blk<qs::kINDI>;
+        const int oe[7] = {E::P0, E::P1, E::P2, E::P3, E::META, E::DA, E::DB}, oi[7] = {I::P0, I::P1, I::P2, I::P3, I::META, -1, -1};
+        memcpy(offsets7, e->variant == QS_E2E ? oe : oi, sizeof oe);
+    }
     return QS_OK;
 }
 
@@ -435,9 +447,20 @@ int qs_step(qs_env *e, const float *actions_dev, float *obs_dev, float *rew_dev,
     P.actions = reinterpret_cast<const float4 *>(actions_dev);
     P.obs = obs_dev; P.rew = rew_dev; P.done = done_dev; P.flags = flags_dev;
     P.mode = mode; P.reset_source = reset_source;
+    // programmatic dependent launch: this grid's prologue may overlap the tail of the previous kernel on the
+    // stream; the kernel itself waits (griddepcontrol.wait) before it touches simulator state
     void *args[] = {&P};
-    QS_CUDA(e, cudaLaunchKernel(step_function(e), dim3((unsigned)e->step_grid), dim3(qs::kBlock), args, e->step_smem,
-                                e->stream));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)e->step_grid);
+    cfg.blockDim = dim3(qs::kStepThreads);
+    cfg.dynamicSmemBytes = e->step_smem;
+    cfg.stream = e->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = e->pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    QS_CUDA(e, cudaLaunchKernelExC(&cfg, step_function(e), args));
     e->launches++;
     QS_CUDA(e, cudaGetLastError());
     return QS_OK;

@@ -35,15 +35,24 @@ struct Stats {  // must match qs_stats
     unsigned long long env_steps, dones, truncated, gates_passed, gate_collisions, ground_collisions, out_of_bounds;
 };
 
-struct Planes {
-    float4 *p0, *p1, *p2;
-    float4 *p3;      // E2E motor speeds
-    float *p3s;      // INDI T_norm
-    float4 *da;      // E2E (Mx,My,Mz,Fz)
-    float2 *db;      // E2E (Fx,Fy)
-    uint32_t *meta;  // target_gate<<24 | step_count
-    uint32_t *episode;
+// Simulator state in HBM: array of structs of arrays, one BLOCK per 32 envs (= one warp).  Inside a block every
+// field is a 32-lane plane of 16-byte words, so a warp's access to a plane is one 512-byte run, and the whole
+// block is ONE contiguous run: a single TMA bulk copy brings all of a warp's state into shared memory.
+template <int V> struct Blk;
+template <> struct Blk<kE2E> {   // bytes: P0=(x,y,z,vx) P1=(vy,vz,phi,theta) P2=(psi,p,q,r) P3=(w1..w4) float4 planes,
+    enum : int { P0 = 0, P1 = 512, P2 = 1024, P3 = 1536, META = 2048, DA = 2176, DB = 2688, BYTES = 2944 };
+};                               // META u32 (target_gate<<24 | step_count), DA=(Mx,My,Mz,Fz) float4, DB=(Fx,Fy) float2
+template <> struct Blk<kINDI> {  // P3 = scalar T_norm plane
+    enum : int { P0 = 0, P1 = 512, P2 = 1024, P3 = 1536, META = 1664, BYTES = 1792, DA = 0, DB = 0 };
 };
+
+struct Planes {
+    unsigned char *base;  // blocks, Blk<V>::BYTES apart
+};
+template <int V, int OFF, typename T>
+__device__ __forceinline__ T &field(const Planes &s, long long env) {
+    return reinterpret_cast<T *>(s.base + (env >> 5) * (long long)Blk<V>::BYTES + OFF)[env & 31];
+}
 
 struct ResetDist {   // reset_ draw ranges (`:455-489`)
     float start[3];
@@ -58,10 +67,14 @@ struct StepParams {
     uint8_t *done;
     uint8_t *flags;
     const float *track;  // (n_gates, kTrackRow): gx gy gz yaw cos sin 0 0 | rel_x rel_y rel_z rel_yaw
-    Stats *stats;
+    Stats *stats;        // one slot per CTA of the step kernel (or NULL)
     long long n;
     long long env_offset;
     unsigned long long seed;
+    // Time half of the RNG key: number of step / reset launches so far.  It lives in DEVICE memory (epoch[0]) so that
+    // a CUDA graph replaying the same launch draws fresh values; the last CTA of a launch to finish (epoch[1] counts
+    // arrivals) advances it, i.e. after every CTA of this launch has read it and before the next launch may.
+    unsigned long long *epoch;
     int n_gates, gates_ahead, obs_len;
     int mode, reset_source;
     uint32_t max_steps;
@@ -133,46 +146,59 @@ struct EnvState {
 
 template <int V>
 __device__ __forceinline__ void load_state(const Planes &s, long long i, EnvState<V> &e) {
-    const float4 a = s.p0[i], b = s.p1[i], c = s.p2[i];
+    using B = Blk<V>;
+    const float4 a = field<V, B::P0, float4>(s, i), b = field<V, B::P1, float4>(s, i), c = field<V, B::P2, float4>(s, i);
     e.x = a.x; e.y = a.y; e.z = a.z; e.vx = a.w;
     e.vy = b.x; e.vz = b.y; e.phi = b.z; e.th = b.w;
     e.psi = c.x; e.p = c.y; e.q = c.z; e.r = c.w;
     if (V == kE2E) {
-        const float4 d = s.p3[i];
+        const float4 d = field<V, B::P3, float4>(s, i);
         e.w[0] = d.x; e.w[1] = d.y; e.w[2] = d.z; e.w[V == kE2E ? 3 : 0] = d.w;
-        const float4 da = s.da[i];
-        const float2 db = s.db[i];
+        const float4 da = field<V, B::DA, float4>(s, i);
+        const float2 db = field<V, B::DB, float2>(s, i);
         e.dist[0] = da.x; e.dist[1] = da.y; e.dist[2] = da.z; e.dist[5] = da.w;
         e.dist[3] = db.x; e.dist[4] = db.y;
     } else {
-        e.w[0] = s.p3s[i];
+        e.w[0] = field<V, B::P3, float>(s, i);
     }
 }
 
 template <int V>
 __device__ __forceinline__ void store_world(const Planes &s, long long i, const EnvState<V> &e) {
-    s.p0[i] = make_float4(e.x, e.y, e.z, e.vx);
-    s.p1[i] = make_float4(e.vy, e.vz, e.phi, e.th);
-    s.p2[i] = make_float4(e.psi, e.p, e.q, e.r);
-    if (V == kE2E) s.p3[i] = make_float4(e.w[0], e.w[1], e.w[2], e.w[V == kE2E ? 3 : 0]);
-    else s.p3s[i] = e.w[0];
+    using B = Blk<V>;
+    field<V, B::P0, float4>(s, i) = make_float4(e.x, e.y, e.z, e.vx);
+    field<V, B::P1, float4>(s, i) = make_float4(e.vy, e.vz, e.phi, e.th);
+    field<V, B::P2, float4>(s, i) = make_float4(e.psi, e.p, e.q, e.r);
+    if (V == kE2E) field<V, B::P3, float4>(s, i) = make_float4(e.w[0], e.w[1], e.w[2], e.w[V == kE2E ? 3 : 0]);
+    else field<V, B::P3, float>(s, i) = e.w[0];
 }
 
 template <int V>
 __device__ __forceinline__ void store_dist(const Planes &s, long long i, const EnvState<V> &e) {
     if (V == kE2E) {
-        s.da[i] = make_float4(e.dist[0], e.dist[1], e.dist[2], e.dist[5]);
-        s.db[i] = make_float2(e.dist[3], e.dist[4]);
+        field<V, Blk<V>::DA, float4>(s, i) = make_float4(e.dist[0], e.dist[1], e.dist[2], e.dist[5]);
+        field<V, Blk<V>::DB, float2>(s, i) = make_float2(e.dist[3], e.dist[4]);
     }
 }
 
 // reset_ (`:452-489`) with the device RNG: same fields, same ranges, counter-based instead of MT19937.
-// Draw c of env g in episode ep is Philox4x32-10(counter=(g_lo,g_hi,ep,c), key=seed): 6 draws (E2E) / 4 (INDI).
+// Draw c of env g reset at launch `epoch` is Philox4x32-10(counter=(g_lo, g_hi, epoch_lo, epoch_hi<<3 | c), key=seed):
+// 6 draws (E2E) / 4 (INDI).  An env resets at most once per launch, so (g, epoch) names the event; nothing
+// per-env has to be stored or read, and the stream does not depend on how N is sharded.
 template <int V> struct ResetDraws { enum : int { N = (V == kE2E ? 6 : 4) }; };
 
-__device__ __forceinline__ uint4 reset_draw(const StepParams &P, unsigned long long g, uint32_t episode, uint32_t c) {
-    return philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), episode, c),
+__device__ __forceinline__ uint4 reset_draw(const StepParams &P, unsigned long long g, uint32_t c) {
+    const unsigned long long epoch = *reinterpret_cast<const volatile unsigned long long *>(P.epoch);
+    return philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)epoch, ((uint32_t)(epoch >> 32) << 3) | c),
                          make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
+}
+// end of a launch that may have drawn resets: called by ONE thread per CTA after its last draw
+__device__ __forceinline__ void epoch_arrive(const StepParams &P) {
+    __threadfence();
+    if (atomicAdd(reinterpret_cast<unsigned long long *>(P.epoch) + 1, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+        P.epoch[1] = 0;
+        P.epoch[0] = P.epoch[0] + 1;
+    }
 }
 
 template <int V>
@@ -200,47 +226,49 @@ __device__ __forceinline__ void fill_reset(const StepParams &P, const uint4 (&r)
 
 // every lane draws for itself (used by reset(), and by the step when many lanes of a warp terminate at once)
 template <int V>
-__device__ __forceinline__ void draw_reset(const StepParams &P, long long env, uint32_t episode, EnvState<V> &e) {
+__device__ __forceinline__ void draw_reset(const StepParams &P, long long env, EnvState<V> &e) {
     const unsigned long long g = (unsigned long long)(env + P.env_offset);
     uint4 r[6];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) r[c] = c < ResetDraws<V>::N ? reset_draw(P, g, episode, c) : make_uint4(0, 0, 0, 0);
+    for (int c = 0; c < 6; ++c) r[c] = c < ResetDraws<V>::N ? reset_draw(P, g, c) : make_uint4(0, 0, 0, 0);
     fill_reset<V>(P, r, e);
 }
 
-// Warp-cooperative form for the common case of one or two terminating lanes per warp: instead of one lane
-// running 6 Philox evaluations while 31 wait, lanes 0..5 each run ONE for that env and hand the words over by
-// shuffle.  Must be called by the whole warp; `need` marks the lanes that reset.  Same values as draw_reset.
+// Warp-cooperative form for the common case of a few terminating lanes per warp: instead of one lane running 6
+// Philox evaluations while 31 wait, lane L evaluates block L % ND for the (L / ND)-th terminating lane -- ONE
+// Philox pass serves up to 32/ND resets -- and the words change hands through 512 bytes of the warp's own shared
+// memory (`scratch`, 16-byte aligned).  Must be called by the whole warp with warp_env0 = env index of lane 0;
+// `need` marks the lanes that reset.  Same values as draw_reset.
 template <int V>
-__device__ __forceinline__ void draw_reset_warp(const StepParams &P, long long env, uint32_t episode, bool need,
+__device__ __forceinline__ void draw_reset_warp(const StepParams &P, long long warp_env0, bool need, uint4 *scratch,
                                                 EnvState<V> &e) {
+    constexpr int ND = ResetDraws<V>::N;
     const unsigned full = 0xffffffffu;
-    unsigned m = __ballot_sync(full, need);
+    const unsigned m = __ballot_sync(full, need);
     if (m == 0) return;
-    if (__popc(m) > 4) {  // mass termination (e.g. synchronous time-outs): per-lane is cheaper
-        if (need) draw_reset<V>(P, env, episode, e);
+    const unsigned lane = threadIdx.x & 31;
+    const int cnt = __popc(m);
+    if (cnt * ND > 32) {  // mass termination (e.g. synchronous time-outs): per-lane is cheaper
+        if (need) draw_reset<V>(P, warp_env0 + lane, e);
         return;
     }
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned long long g_own = (unsigned long long)(env + P.env_offset);
-    while (m) {
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        const uint32_t g_lo = __shfl_sync(full, (uint32_t)g_own, src), g_hi = __shfl_sync(full, (uint32_t)(g_own >> 32), src);
-        const uint32_t ep = __shfl_sync(full, episode, src);
-        const uint4 mine = reset_draw(P, ((unsigned long long)g_hi << 32) | g_lo, ep, lane & 7);
+    const int which = lane / ND, c = lane - which * ND;
+    unsigned mm = m;  // lane index of the `which`-th terminating lane
+#pragma unroll
+    for (int k = 0; k < 32 / ND - 1; ++k) mm = (k < which) ? (mm & (mm - 1)) : mm;
+    if (which < cnt) {
+        const int src = __ffs(mm) - 1;
+        scratch[lane] = reset_draw(P, (unsigned long long)(warp_env0 + src + P.env_offset), c);
+    }
+    __syncwarp();
+    if (need) {
+        const int rank = __popc(m & ((1u << lane) - 1u));
         uint4 r[6];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
-            if (c < ResetDraws<V>::N) {
-                r[c].x = __shfl_sync(full, mine.x, c); r[c].y = __shfl_sync(full, mine.y, c);
-                r[c].z = __shfl_sync(full, mine.z, c); r[c].w = __shfl_sync(full, mine.w, c);
-            } else {
-                r[c] = make_uint4(0, 0, 0, 0);
-            }
-        }
-        if ((int)lane == src) fill_reset<V>(P, r, e);
+        for (int k = 0; k < 6; ++k) r[k] = k < ND ? scratch[rank * ND + k] : make_uint4(0, 0, 0, 0);
+        fill_reset<V>(P, r, e);
     }
+    __syncwarp();
 }
 
 // update_states_gate for one env (`:365-450`), written to a row in shared memory.
@@ -383,10 +411,14 @@ __device__ __forceinline__ void residual_mlp(const StepParams &P, const float (&
 // coefficients), <= 1.5 ulp on |x| < 1e5 -- the same error class as NumPy's float32 sin/cos (1.45 ulp), see
 // tests/test_kernel_math_models.py.  Huge arguments (a blown-up yaw) take the library's Payne-Hanek path
 // out of line, so the hot code stays small and needs no stack frame.
-__device__ __noinline__ void sincos_slow(float x, float *s, float *c) { sincosf(x, s, c); }
+__device__ __noinline__ float2 sincos_slow(float x) {
+    float s, c;
+    sincosf(x, &s, &c);
+    return make_float2(s, c);
+}
 
 __device__ __forceinline__ void sincos_fast(float x, float &sn, float &cs) {
-    if (fabsf(x) > 1.0e5f) { sincos_slow(x, &sn, &cs); return; }   // also NaN/Inf
+    if (fabsf(x) > 1.0e5f) { const float2 r = sincos_slow(x); sn = r.x; cs = r.y; return; }   // also NaN/Inf
     const float j = rintf(x * 0.636619772367581343f);
     const int q = (int)j;
     float a = fmaf(j, -1.5707962512969970703f, x);
@@ -427,7 +459,11 @@ __device__ __forceinline__ void euler_step(const StepParams &P, const EnvState<V
         const float w1 = e.w[0], w2 = e.w[1], w3 = e.w[2], w4 = e.w[V == kE2E ? 3 : 0];
         const float x[10] = {w1, w2, w3, w4, vbx, vby, vbz, e.p, e.q, e.r};
         float thr, mom[3];
+#ifdef QS_EXP_NOMLP  // experiment only (tools/exp_variants.sh): what the step costs without the residual MLPs
+        thr = x[4] * P.b2[0]; mom[0] = x[5] * P.b2[1]; mom[1] = x[6] * P.b2[2]; mom[2] = x[7] * P.b2[3];
+#else
         residual_mlp(P, x, thr, mom);
+#endif
         const float Mx = mom[0] + e.dist[0], My = mom[1] + e.dist[1], Mz = mom[2] + e.dist[2];
         const float Fz = thr + e.dist[5];
         const float W1 = fmaf(4000.f, w1, 7000.f), W2 = fmaf(4000.f, w2, 7000.f);
@@ -494,6 +530,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// programmatic dependent launch: let the next step's CTAs be scheduled while this grid drains / wait for the
+// previous grid's memory before touching simulator state
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
@@ -511,74 +555,76 @@ __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ the step kernel
-// Input tile of one pipeline stage: the 128 envs of a tile are 2 KB-contiguous in every plane, so a stage is
-// filled by 6-8 bulk copies issued by ONE thread; nobody else spends an instruction on global loads.
-template <int V> struct Stage;
-template <> struct Stage<kE2E> {
-    enum : int { P0 = 0, P1 = 2048, P2 = 4096, P3 = 6144, DA = 8192, DB = 10240, META = 11264, ACT = 11776, BYTES = 13824 };
-};
-template <> struct Stage<kINDI> {
-    enum : int { P0 = 0, P1 = 2048, P2 = 4096, P3 = 6144, META = 6656, ACT = 7168, BYTES = 9216, DA = 0, DB = 0 };
+// Input stage of ONE WARP: the warp's state block exactly as it lies in HBM (one bulk copy) followed by its 32
+// action rows (a second bulk copy from the caller's buffer); nobody spends an instruction on global loads.
+template <int V> struct Stage : Blk<V> {
+    enum : int { ACT = Blk<V>::BYTES, BYTES = Blk<V>::BYTES + 512 };
 };
 constexpr int kBarBytes = 128;  // mbarriers live in the first 128 bytes of dynamic shared memory
+constexpr int kWarps = kBlock / 32;
 
 __host__ __device__ constexpr size_t step_smem_bytes(int variant, int stages, int obs_len, int n_gates) {
-    return kBarBytes + (size_t)stages * (variant == kE2E ? (int)Stage<kE2E>::BYTES : (int)Stage<kINDI>::BYTES) +
+    return kBarBytes + (size_t)stages * kWarps * (variant == kE2E ? (int)Stage<kE2E>::BYTES : (int)Stage<kINDI>::BYTES) +
            (size_t)kBlock * obs_len * 4 + (size_t)n_gates * kTrackRow * 4;
 }
 
+// lane 0 of a warp: fill one of the warp's stages with the 32 envs starting at `first`
 template <int V>
-__device__ __forceinline__ void issue_tile(const StepParams &P, unsigned char *st, uint64_t *bar, long long tile) {
+__device__ __forceinline__ void issue_warp_tile(const StepParams &P, unsigned char *st, uint64_t *bar, long long first) {
     using S = Stage<V>;
-    const long long base = tile * kBlock;
-    const long long rem = P.n - base;
-    const uint32_t act_bytes = (uint32_t)(rem < kBlock ? rem : kBlock) * 16u;  // caller's buffer is not padded
-    mbar_expect_tx(bar, (uint32_t)S::BYTES - 2048u + act_bytes);
-    bulk_load(st + S::P0, P.s.p0 + base, 2048, bar);
-    bulk_load(st + S::P1, P.s.p1 + base, 2048, bar);
-    bulk_load(st + S::P2, P.s.p2 + base, 2048, bar);
-    if (V == kE2E) {
-        bulk_load(st + S::P3, P.s.p3 + base, 2048, bar);
-        bulk_load(st + S::DA, P.s.da + base, 2048, bar);
-        bulk_load(st + S::DB, P.s.db + base, 1024, bar);
-    } else {
-        bulk_load(st + S::P3, P.s.p3s + base, 512, bar);
-    }
-    bulk_load(st + S::META, P.s.meta + base, 512, bar);
-    bulk_load(st + S::ACT, P.actions + base, act_bytes, bar);
+    const long long rem = P.n - first;
+    const uint32_t act_bytes = rem >= 32 ? 512u : (rem > 0 ? (uint32_t)rem * 16u : 0u);  // caller's buffer is not padded
+    mbar_expect_tx(bar, (uint32_t)Blk<V>::BYTES + act_bytes);
+    bulk_load(st, P.s.base + (first >> 5) * (long long)Blk<V>::BYTES, Blk<V>::BYTES, bar);
+    if (act_bytes) bulk_load(st + S::ACT, P.actions + first, act_bytes, bar);
 }
 
-// Persistent CTAs (grid = SMs x resident CTAs), each looping over 128-env tiles through a kStages-deep ring of
-// shared-memory stages: while tile i is being computed, the TMA engine is already filling the stages of the next
-// tiles, so HBM latency never sits on a warp's scoreboard.  Per tile: 1 mbarrier wait, 2 block barriers.
+// Persistent CTAs (grid = SMs x resident CTAs) of four INDEPENDENT warps.  Each warp owns 32 envs of the CTA's
+// 128-env tile and runs its own kStages-deep ring of shared-memory stages: lane 0 refills a stage with TMA bulk
+// loads the moment the warp has copied it to registers, and waits on the stage's mbarrier for the bytes to land.
+// There is no block barrier anywhere in the loop, so the warps of an SM drift apart: while one computes, others
+// load or store.  Observations leave through the warp's slice of the staging tile as one TMA bulk store (32 rows
+// of a row-major (N,D) array are contiguous).
+constexpr int kStepThreads = kBlock;
+
 template <int V, int kStages>
-__global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ StepParams P) {
+__global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel(const __grid_constant__ StepParams P) {
     using S = Stage<V>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
-    unsigned char *stages = smem_raw + kBarBytes;
-    float *s_obs = reinterpret_cast<float *>(stages + kStages * S::BYTES);
-    float *s_track = s_obs + kBlock * P.obs_len;
     const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw) + warp * kStages;          // this warp's barriers
+    unsigned char *stages = smem_raw + kBarBytes + warp * (kStages * S::BYTES);          // this warp's ring
+    float *s_obs = reinterpret_cast<float *>(smem_raw + kBarBytes + kWarps * kStages * S::BYTES);
+    float *s_track = s_obs + kBlock * P.obs_len;
     const long long n_tiles = (P.n + kBlock - 1) / kBlock;
 
-    if (tid == 0) {
+    if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    load_track(P, s_track);  // ends with __syncthreads(): barrier init is visible to everyone
-    if (tid == 0) {
+    for (int i = tid; i < P.n_gates * kTrackRow; i += kStepThreads) s_track[i] = P.track[i];
+    __syncthreads();  // barrier init and track table visible to everyone
+    // Everything above touched only launch constants.  From here on we read and write simulator state that the
+    // previous step's grid may still be producing (programmatic dependent launch).
+    pdl_launch_dependents();
+    pdl_wait();
+    if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) {
             const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
-            if (t < n_tiles) issue_tile<V>(P, stages + s * S::BYTES, &full[s], t);
+            if (t < n_tiles) issue_warp_tile<V>(P, stages + s * S::BYTES, &full[s], t * kBlock + warp * 32);
         }
     }
 
+    // ------------------------------------------------------------------------------------------ consumers
     float reward_acc = 0.0f;  // stats are reduced once per CTA lifetime, not per tile
     unsigned c_act = 0, c_done = 0, c_tr = 0, c_gp = 0, c_gc = 0, c_gr = 0, c_ob = 0;
     const bool write_obs_tile = P.mode != kModePause;
+    float *const my_obs = s_obs + tid * P.obs_len;
+    const float *const warp_obs = s_obs + warp * 32 * P.obs_len;
+    bool obs_in_flight = false;  // warp-uniform: a bulk store of this warp's observation slice may still be reading it
     int it = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int stage = it % kStages;
@@ -588,34 +634,37 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ St
         const bool active = env < P.n;
         mbar_wait(&full[stage], (uint32_t)(it / kStages) & 1u);
 
-        // ---- stage -> registers (conflict-free: consecutive threads read consecutive 16-byte words)
+        // ---- stage -> registers (conflict-free: consecutive lanes read consecutive 16-byte words)
         EnvState<V> e, n;
         {
-            const float4 a = reinterpret_cast<const float4 *>(st + S::P0)[tid];
-            const float4 b = reinterpret_cast<const float4 *>(st + S::P1)[tid];
-            const float4 c = reinterpret_cast<const float4 *>(st + S::P2)[tid];
+            const float4 a = reinterpret_cast<const float4 *>(st + S::P0)[lane];
+            const float4 b = reinterpret_cast<const float4 *>(st + S::P1)[lane];
+            const float4 c = reinterpret_cast<const float4 *>(st + S::P2)[lane];
             e.x = a.x; e.y = a.y; e.z = a.z; e.vx = a.w; e.vy = b.x; e.vz = b.y; e.phi = b.z; e.th = b.w;
             e.psi = c.x; e.p = c.y; e.q = c.z; e.r = c.w;
             if (V == kE2E) {
-                const float4 d = reinterpret_cast<const float4 *>(st + S::P3)[tid];
-                const float4 da = reinterpret_cast<const float4 *>(st + S::DA)[tid];
-                const float2 db = reinterpret_cast<const float2 *>(st + S::DB)[tid];
+                const float4 d = reinterpret_cast<const float4 *>(st + S::P3)[lane];
+                const float4 da = reinterpret_cast<const float4 *>(st + S::DA)[lane];
+                const float2 db = reinterpret_cast<const float2 *>(st + S::DB)[lane];
                 e.w[0] = d.x; e.w[1] = d.y; e.w[2] = d.z; e.w[V == kE2E ? 3 : 0] = d.w;
                 e.dist[0] = da.x; e.dist[1] = da.y; e.dist[2] = da.z; e.dist[5] = da.w; e.dist[3] = db.x; e.dist[4] = db.y;
             } else {
-                e.w[0] = reinterpret_cast<const float *>(st + S::P3)[tid];
+                e.w[0] = reinterpret_cast<const float *>(st + S::P3)[lane];
             }
         }
-        const float4 u = reinterpret_cast<const float4 *>(st + S::ACT)[tid];
-        const uint32_t meta = reinterpret_cast<const uint32_t *>(st + S::META)[tid];
+        const float4 u = reinterpret_cast<const float4 *>(st + S::ACT)[lane];
+        const uint32_t meta = reinterpret_cast<const uint32_t *>(st + S::META)[lane];
         uint32_t tg = meta >> 24, sc = meta & kStepMask;
-        if (tid == 0 && it > 0 && write_obs_tile) bulk_store_wait_read();  // previous tile's obs has left s_obs
-        __syncthreads();  // [A] every thread holds its inputs: the stage and s_obs may be overwritten
-        if (tid == 0) {
+        __syncwarp();  // the warp's inputs are in registers: refill the stage with the tile kStages ahead
+        if (lane == 0) {
             const long long nt = tile + (long long)kStages * gridDim.x;
-            if (nt < n_tiles) issue_tile<V>(P, st, &full[stage], nt);
+            if (nt < n_tiles) issue_warp_tile<V>(P, st, &full[stage], nt * kBlock + warp * 32);
         }
 
+#ifdef QS_EXP_NOCOMPUTE  // experiment only: the memory pipeline alone (same loads and stores, no arithmetic)
+        n = e; n.x = e.x + u.x; n.y = e.y + u.y + u.z + u.w;
+        float reward = u.y; const bool dn = false; const uint32_t fl = 0;
+#else
         euler_step<V>(P, e, u, n);
         sc = sc < kStepMask ? sc + 1 : sc;  // step_counts += 1 (`:514`), saturating in 24 bits
 
@@ -642,17 +691,21 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ St
         const bool dn = trunc | ground | collided | oob;
         const uint32_t fl = (dn ? F_DONE : 0u) | (trunc ? F_TRUNC : 0u) | (passed ? F_PASSED : 0u) |
                             (collided ? F_COLLISION : 0u) | (ground ? F_GROUND : 0u) | (oob ? F_OOB : 0u);
+#endif
 
         // ---- branch logic (`:568-585`)
         bool write_world = active, write_dist = false;
         if (P.mode == kModeNormal) {
-            if (P.reset_source == kResetDevice) {  // block-uniform branch: the whole warp takes part in the draw
+            if (P.reset_source == kResetDevice) {  // warp-uniform branch: the whole warp takes part in the draw
                 const bool need = dn && active;
-                uint32_t ep = 0;
-                if (need) ep = P.s.episode[env];
-                draw_reset_warp<V>(P, env, ep, need, n);
+                // scratch = the head of this warp's observation slice: its previous bulk store must have been read
+                if (__any_sync(0xffffffffu, need)) {
+                    if (lane == 0 && obs_in_flight) bulk_store_wait_read();
+                    obs_in_flight = false;
+                    __syncwarp();
+                    draw_reset_warp<V>(P, base + warp * 32, need, reinterpret_cast<uint4 *>(s_obs + warp * 32 * P.obs_len), n);
+                }
                 if (need) {
-                    P.s.episode[env] = ep + 1;
                     tg = 0; sc = 0;
                     write_dist = (V == kE2E);
                 }
@@ -662,29 +715,51 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ St
         } else {  // env.pause
             write_world = false;
         }
+        unsigned char *const gblk = P.s.base + (tile * kWarps + warp) * (long long)Blk<V>::BYTES;  // this warp's block
         if (active) {
-            P.s.meta[env] = (tg << 24) | sc;
+            reinterpret_cast<uint32_t *>(gblk + S::META)[lane] = (tg << 24) | sc;
             P.rew[env] = reward;
             P.done[env] = (P.mode == kModePause) ? (uint8_t)0 : (uint8_t)(dn ? 1 : 0);
             if (P.flags) P.flags[env] = (uint8_t)fl;
         }
-        if (write_world) store_world<V>(P.s, env, n);
-        if (write_dist) store_dist<V>(P.s, env, n);
+        if (write_world) {
+            reinterpret_cast<float4 *>(gblk + S::P0)[lane] = make_float4(n.x, n.y, n.z, n.vx);
+            reinterpret_cast<float4 *>(gblk + S::P1)[lane] = make_float4(n.vy, n.vz, n.phi, n.th);
+            reinterpret_cast<float4 *>(gblk + S::P2)[lane] = make_float4(n.psi, n.p, n.q, n.r);
+            if (V == kE2E) reinterpret_cast<float4 *>(gblk + S::P3)[lane] = make_float4(n.w[0], n.w[1], n.w[2], n.w[V == kE2E ? 3 : 0]);
+            else reinterpret_cast<float *>(gblk + S::P3)[lane] = n.w[0];
+        }
+        if (V == kE2E && write_dist) {
+            reinterpret_cast<float4 *>(gblk + S::DA)[lane] = make_float4(n.dist[0], n.dist[1], n.dist[2], n.dist[5]);
+            reinterpret_cast<float2 *>(gblk + S::DB)[lane] = make_float2(n.dist[3], n.dist[4]);
+        }
 
         if (write_obs_tile) {
-            write_obs<V>(P, s_track, n, tg, s_obs + tid * P.obs_len);
-            const long long rem = P.n - base;
-            const int rows = rem < kBlock ? (int)rem : kBlock;
-            float *dst = P.obs + base * P.obs_len;
+            if (lane == 0 && obs_in_flight) bulk_store_wait_read();  // the previous tile's rows have left this warp's slice
+            __syncwarp();
+#ifdef QS_EXP_NOCOMPUTE
+            if (V == kE2E) {
+                for (int k = 0; k < P.obs_len; k += 4) *reinterpret_cast<float4 *>(my_obs + k) = make_float4(n.x, n.y, n.z, n.vx);
+            } else {
+                for (int k = 0; k < P.obs_len; ++k) my_obs[k] = n.x;
+            }
+#else
+            write_obs<V>(P, s_track, n, tg, my_obs);
+#endif
+            const long long rem = P.n - (base + warp * 32);
+            const int rows = rem < 32 ? (rem < 0 ? 0 : (int)rem) : 32;
+            float *dst = P.obs + (base + warp * 32) * P.obs_len;
             const uint32_t bytes = (uint32_t)rows * (uint32_t)P.obs_len * 4u;
             const bool bulk = ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) && ((bytes & 15u) == 0);
-            if (bulk) {  // the tile's rows are contiguous in the (N,D) output: one TMA bulk store
+            if (bulk) {  // the warp's rows are contiguous in the (N,D) output: one TMA bulk store
                 fence_proxy_async();
-                __syncthreads();  // [B]
-                if (tid == 0) bulk_store(dst, s_obs, bytes);
+                __syncwarp();
+                if (lane == 0 && bytes) bulk_store(dst, warp_obs, bytes);
+                obs_in_flight = true;
             } else {
-                __syncthreads();
-                for (int i = tid; i < rows * P.obs_len; i += kBlock) dst[i] = s_obs[i];
+                __syncwarp();
+                for (int i = lane; i < rows * P.obs_len; i += 32) dst[i] = warp_obs[i];
+                __syncwarp();
             }
         }
         if (P.stats && active) {
@@ -693,9 +768,14 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ St
             c_gc += (fl & F_COLLISION) != 0; c_gr += (fl & F_GROUND) != 0; c_ob += (fl & F_OOB) != 0;
         }
     }
-    if (tid == 0 && write_obs_tile) bulk_store_wait_read();  // shared memory must outlive the last bulk read
+    if (lane == 0 && write_obs_tile) bulk_store_wait_read();  // shared memory must outlive the last bulk read
+    __syncthreads();  // every warp of the CTA is past its last reset draw
+    if (tid == 0) epoch_arrive(P);
 
-    if (P.stats) {  // warp-level reduction of the reward and the flag counters, one atomic set per warp
+    if (P.stats) {  // warp-shuffle reduction, then ONE plain read-modify-write per CTA on the CTA's own slot:
+                    // no atomics (740-1184 CTAs hammering one address cost 1-4 us per launch), summed by qs_get_stats
+        __shared__ float s_red_f[kBlock / 32];
+        __shared__ unsigned s_red_u[kBlock / 32][7];
         const unsigned full_mask = 0xffffffffu;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) reward_acc += __shfl_xor_sync(full_mask, reward_acc, o);
@@ -703,15 +783,28 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ St
         c_tr = __reduce_add_sync(full_mask, c_tr); c_gp = __reduce_add_sync(full_mask, c_gp);
         c_gc = __reduce_add_sync(full_mask, c_gc); c_gr = __reduce_add_sync(full_mask, c_gr);
         c_ob = __reduce_add_sync(full_mask, c_ob);
-        if ((tid & 31) == 0 && c_act) {
-            atomicAdd(&P.stats->reward_sum, (double)reward_acc);
-            atomicAdd(&P.stats->env_steps, (unsigned long long)c_act);
-            if (c_done) atomicAdd(&P.stats->dones, (unsigned long long)c_done);
-            if (c_tr) atomicAdd(&P.stats->truncated, (unsigned long long)c_tr);
-            if (c_gp) atomicAdd(&P.stats->gates_passed, (unsigned long long)c_gp);
-            if (c_gc) atomicAdd(&P.stats->gate_collisions, (unsigned long long)c_gc);
-            if (c_gr) atomicAdd(&P.stats->ground_collisions, (unsigned long long)c_gr);
-            if (c_ob) atomicAdd(&P.stats->out_of_bounds, (unsigned long long)c_ob);
+        if ((tid & 31) == 0) {
+            const int w = tid >> 5;
+            s_red_f[w] = reward_acc;
+            s_red_u[w][0] = c_act; s_red_u[w][1] = c_done; s_red_u[w][2] = c_tr; s_red_u[w][3] = c_gp;
+            s_red_u[w][4] = c_gc; s_red_u[w][5] = c_gr; s_red_u[w][6] = c_ob;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float r = 0.0f;
+            unsigned c[7] = {0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int w = 0; w < kBlock / 32; ++w) {
+                r += s_red_f[w];
+#pragma unroll
+                for (int k = 0; k < 7; ++k) c[k] += s_red_u[w][k];
+            }
+            if (c[0]) {
+                Stats *st = P.stats + blockIdx.x;
+                st->reward_sum += (double)r;
+                st->env_steps += c[0]; st->dones += c[1]; st->truncated += c[2]; st->gates_passed += c[3];
+                st->gate_collisions += c[4]; st->ground_collisions += c[5]; st->out_of_bounds += c[6];
+            }
         }
     }
 }
@@ -730,21 +823,20 @@ __global__ void __launch_bounds__(kBlock) observe_kernel(const __grid_constant__
         EnvState<V> e;
         uint32_t tg;
         if (reset_all) {
-            const uint32_t ep = P.s.episode[env];
-            draw_reset<V>(P, env, ep, e);
-            P.s.episode[env] = ep + 1;
+            draw_reset<V>(P, env, e);
             tg = 0;
-            P.s.meta[env] = 0;
+            field<V, Blk<V>::META, uint32_t>(P.s, env) = 0;
             store_world<V>(P.s, env, e);
             store_dist<V>(P.s, env, e);
         } else {
             load_state<V>(P.s, env, e);
-            tg = P.s.meta[env] >> 24;
+            tg = field<V, Blk<V>::META, uint32_t>(P.s, env) >> 24;
         }
         write_obs<V>(P, s_track, e, tg, s_obs + threadIdx.x * P.obs_len);
     }
     const long long rem = P.n - base;
-    store_obs_tile(P.obs + base * P.obs_len, s_obs, rem < kBlock ? (int)rem : kBlock, P.obs_len);
+    store_obs_tile(P.obs + base * P.obs_len, s_obs, rem < kBlock ? (int)rem : kBlock, P.obs_len);  // block barrier inside
+    if (reset_all && threadIdx.x == 0) epoch_arrive(P);
 }
 
 // Masked stores of reset_ with host-drawn values (`:476-489`) + the observation rows of those envs.
@@ -771,13 +863,13 @@ __global__ void __launch_bounds__(kBlock) apply_reset_kernel(const __grid_consta
             for (int j = 0; j < 6; ++j) e.dist[j] = dist[k * 6 + j];
             store_dist<V>(P.s, env, e);
         } else {
-            const float4 da = P.s.da[env];
-            const float2 db = P.s.db[env];
+            const float4 da = field<V, Blk<V>::DA, float4>(P.s, env);
+            const float2 db = field<V, Blk<V>::DB, float2>(P.s, env);
             e.dist[0] = da.x; e.dist[1] = da.y; e.dist[2] = da.z; e.dist[5] = da.w; e.dist[3] = db.x; e.dist[4] = db.y;
         }
     }
     store_world<V>(P.s, env, e);
-    P.s.meta[env] = 0;
+    field<V, Blk<V>::META, uint32_t>(P.s, env) = 0;
     float *row = s_obs + threadIdx.x * P.obs_len;
     write_obs<V>(P, s_track, e, 0u, row);
     float *dst = P.obs + env * P.obs_len;
@@ -791,26 +883,27 @@ __global__ void import_kernel(Planes s, long long first, long long count, const 
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
     const long long env = first + k;
+    using B = Blk<V>;
     constexpr int NS = V == kE2E ? 16 : 13;
     if (ws) {
         const float *r = ws + k * NS;
-        s.p0[env] = make_float4(r[0], r[1], r[2], r[3]);
-        s.p1[env] = make_float4(r[4], r[5], r[6], r[7]);
-        s.p2[env] = make_float4(r[8], r[9], r[10], r[11]);
-        if (V == kE2E) s.p3[env] = make_float4(r[12], r[13], r[14], r[V == kE2E ? 15 : 12]);
-        else s.p3s[env] = r[12];
+        field<V, B::P0, float4>(s, env) = make_float4(r[0], r[1], r[2], r[3]);
+        field<V, B::P1, float4>(s, env) = make_float4(r[4], r[5], r[6], r[7]);
+        field<V, B::P2, float4>(s, env) = make_float4(r[8], r[9], r[10], r[11]);
+        if (V == kE2E) field<V, B::P3, float4>(s, env) = make_float4(r[12], r[13], r[14], r[V == kE2E ? 15 : 12]);
+        else field<V, B::P3, float>(s, env) = r[12];
     }
     if (V == kE2E && dist) {
         const float *d = dist + k * 6;
-        s.da[env] = make_float4(d[0], d[1], d[2], d[5]);
-        s.db[env] = make_float2(d[3], d[4]);
+        field<V, B::DA, float4>(s, env) = make_float4(d[0], d[1], d[2], d[5]);
+        field<V, B::DB, float2>(s, env) = make_float2(d[3], d[4]);
     }
     if (tg || sc) {
-        const uint32_t m = s.meta[env];
+        const uint32_t m = field<V, B::META, uint32_t>(s, env);
         uint32_t g = m >> 24, c = m & kStepMask;
         if (tg) { long long t = tg[k] % n_gates; if (t < 0) t += n_gates; g = (uint32_t)t; }
         if (sc) { long long v = sc[k]; c = v < 0 ? 0u : (v > (long long)kStepMask ? kStepMask : (uint32_t)v); }
-        s.meta[env] = (g << 24) | c;
+        field<V, B::META, uint32_t>(s, env) = (g << 24) | c;
     }
 }
 
@@ -820,23 +913,24 @@ __global__ void export_kernel(Planes s, long long first, long long count, float 
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
     const long long env = first + k;
+    using B = Blk<V>;
     constexpr int NS = V == kE2E ? 16 : 13;
     if (ws) {
         float *r = ws + k * NS;
-        const float4 a = s.p0[env], b = s.p1[env], c = s.p2[env];
+        const float4 a = field<V, B::P0, float4>(s, env), b = field<V, B::P1, float4>(s, env), c = field<V, B::P2, float4>(s, env);
         r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
         r[8] = c.x; r[9] = c.y; r[10] = c.z; r[11] = c.w;
-        if (V == kE2E) { const float4 d = s.p3[env]; r[12] = d.x; r[13] = d.y; r[14] = d.z; r[V == kE2E ? 15 : 12] = d.w; }
-        else r[12] = s.p3s[env];
+        if (V == kE2E) { const float4 d = field<V, B::P3, float4>(s, env); r[12] = d.x; r[13] = d.y; r[14] = d.z; r[V == kE2E ? 15 : 12] = d.w; }
+        else r[12] = field<V, B::P3, float>(s, env);
     }
     if (V == kE2E && dist) {
-        const float4 da = s.da[env];
-        const float2 db = s.db[env];
+        const float4 da = field<V, B::DA, float4>(s, env);
+        const float2 db = field<V, B::DB, float2>(s, env);
         float *d = dist + k * 6;
         d[0] = da.x; d[1] = da.y; d[2] = da.z; d[3] = db.x; d[4] = db.y; d[5] = da.w;
     }
     if (tg || sc) {
-        const uint32_t m = s.meta[env];
+        const uint32_t m = field<V, B::META, uint32_t>(s, env);
         if (tg) tg[k] = m >> 24;
         if (sc) sc[k] = m & kStepMask;
     }

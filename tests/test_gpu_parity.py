@@ -271,6 +271,70 @@ def test_device_rng_is_shard_invariant(variant, tracks):
         np.testing.assert_array_equal(of, np.concatenate([oa, ob]))
 
 
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_device_rng_advances_every_launch_also_under_graph_replay(variant, tracks):
+    """The RNG's launch epoch lives in device memory: every launch (also the SAME captured launch replayed by a
+    CUDA graph) draws fresh reset values, and qs_seed rewinds the stream."""
+    import torch
+    n = 1000  # ragged tail tile, several warps with > 32/ND resets (per-lane path) since every env times out
+    env = make_env(variant, n, tracks, reset_rng="device", seed=11)
+    env.max_steps = 1
+    env.reset_tensor()
+    a = torch.zeros((n, 4), device="cuda")
+    seen = []
+    for _ in range(3):
+        env.step_tensor(a)
+        seen.append(env.world_states.copy())
+    assert not np.array_equal(seen[0], seen[1]) and not np.array_equal(seen[1], seen[2])
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        env.step_tensor(a)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        env.step_tensor(a)
+    reps = []
+    for _ in range(3):
+        g.replay()
+        torch.cuda.synchronize()
+        reps.append(env.world_states.copy())
+    assert not np.array_equal(reps[0], reps[1]) and not np.array_equal(reps[1], reps[2])
+    sp = env.start_pos
+    for ws in reps:  # still the reset distribution
+        assert (np.abs(ws[:, 0:3] - sp) <= 0.5 + 1e-6).all() and np.unique(ws[:, 0]).size > n // 2
+    # same seed, same call sequence => same values
+    env._call("qs_seed", 11)
+    env.reset_tensor()
+    env.step_tensor(a)
+    np.testing.assert_array_equal(env.world_states, seen[0])
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_few_resets_per_warp_use_cooperative_draw_and_match_per_lane_draw(variant, tracks):
+    """Warp-cooperative reset (<= 32/ND terminating lanes per warp) and the per-lane fallback (mass termination)
+    are the same function of (seed, env, epoch): force both on the same envs and compare."""
+    n = 4096
+    ws, tg, sc, act, dist = oracle_inputs(variant, n, tracks, seed=3)
+    outs = []
+    for dense in (False, True):
+        env = make_env(variant, n, tracks, reset_rng="device", seed=21)
+        env.max_steps = 50
+        force(env, ws, tg, np.full(n, 10), dist)
+        sc2 = np.full(n, 10)
+        pick = np.arange(n) % 32 == 5 if not dense else np.ones(n, bool)   # 1 lane per warp | every lane
+        sc2[pick] = 49                                                       # those time out in this step
+        env.step_counts = sc2
+        env.update_states()
+        import torch
+        _, _, done, _ = env.step_tensor(torch.from_numpy(act).cuda())
+        d = done.cpu().numpy().astype(bool)
+        assert d[pick].all()
+        outs.append((env.world_states, d))
+    sel = np.arange(n) % 32 == 5
+    np.testing.assert_array_equal(outs[0][0][sel], outs[1][0][sel])
+
+
 def test_c_abi_host_step_matches_device_step(tracks):
     """qs_step_host (HOST buffers in/out) == qs_step on device buffers."""
     import ctypes as C
