@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather-obs", action="store_true", help="add the NCCL all-gather of observations per step")
+    ap.add_argument("--workload", default="step", choices=["step", "policy", "rollout"],
+                    help="step: the env step alone on resident actions (the headline, default); policy: the on-device "
+                         "controller forward alone (tcgen05); rollout: policy forward + env step per step, no host")
     ap.add_argument("--no-stats", action="store_true", help="do not accumulate the device-side reward/flag totals")
     ap.add_argument("--graph", type=int, default=20,
                     help="replay the timed steps as a CUDA graph of this many steps (0 = one launch call per step)")
@@ -65,6 +68,7 @@ def cpu_step_rate(variant, n_envs, gates_ahead, seconds, min_steps=3):
     import optimal_quad_control_rl_b200 as Q
     from oracle import c_oracle as O
 
+    O.lib().qo_set_num_threads(os.cpu_count() or 1)  # all host threads, whatever OMP_NUM_THREADS the launcher set
     gp, gy, sp = track_for(variant)
     env = O.OracleEnv(variant, n_envs, gp, gy, sp, gates_ahead=gates_ahead)
     if variant == "e2e":
@@ -95,6 +99,7 @@ def run_reference(a):
     import optimal_quad_control_rl_b200 as Q
     from oracle import c_oracle as O
 
+    O.lib().qo_set_num_threads(os.cpu_count() or 1)  # all host threads (torchrun exports OMP_NUM_THREADS=1)
     gp, gy, sp = track_for(a.variant)
     env = O.OracleEnv(a.variant, a.cpu_envs, gp, gy, sp, gates_ahead=a.gates_ahead)
     if a.variant == "e2e":
@@ -205,7 +210,19 @@ def run_ours(a):
     if a.gather_obs:
         gather = Q.ObsAllGather(n * world, env.state_len, dev)
 
+    pol = None
+    if a.workload != "step":
+        if a.variant != "e2e" or ga != 1:
+            raise SystemExit("--workload policy/rollout uses the shipped 24-input controller: e2e, --gates-ahead 1")
+        pol = Q.MlpPolicy.from_npz(device=dev, seed=3, env_offset=rank * n)
+        obs_in = [torch.randn((n, env.state_len), generator=gen, device=dev) for _ in range(4)]
+
     def one_step(i):
+        if a.workload == "policy":
+            pol.forward(obs_in[i & 3], out=acts[i & 3])
+            return
+        if a.workload == "rollout":  # actions come from the controller evaluated on the previous observations
+            pol.forward(env._obs_ring[env._ring], out=acts[i & 3])
         env.step_tensor(acts[i & 3], obs_out=None if gather is None else gather.local_slot())
         if gather is not None:
             gather.gather()
@@ -256,12 +273,46 @@ def run_ours(a):
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     launches = env.launch_count - l0 if graph is None else K  # graph replays launch the same kernels
+    if a.workload == "policy":
+        launches = K
+    elif a.workload == "rollout":
+        launches = 2 * K
     st = env.stats(reset=True)
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
     value = n * world * K / (ms * 1e-3)
+
+    if a.workload != "step":
+        if rank == 0:
+            flops = 2.0 * sum(w.size for w in pol.weights)  # algorithmic MACs of the unpadded network x 2
+            peaks = {}
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                    peaks = json.load(f)
+            except Exception:
+                pass
+            tf_peak = float(peaks.get("bf16_tflops_sustained", 1407.0))
+            out = {"metric": METRIC if a.workload == "rollout" else "policy forwards/sec", "value": value,
+                   "unit": UNIT if a.workload == "rollout" else "obs/s", "n_gpus": world, "steps": K, "warmup": W,
+                   "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                   "dtype": "bf16 operands / f32 accumulate (policy), f32 (env)", "data": "synthetic",
+                   "config": {"workload": a.workload + "_" + workload_name(a), "policy": "24-120-120-120-4 ReLU "
+                              "(c_code/neural_network.c weights), Gaussian noise + clip", "envs_per_gpu": n,
+                              "launch": "cuda-graph x%d" % a.graph if graph is not None else "per-step"},
+                   "clocks": clocks, "gpu_launches": int(launches), "e2e": None}
+            if a.workload == "policy":
+                ach = n * flops / (ms / K * 1e-3) / 1e12
+                out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
+                                   "frac": ach / tf_peak, "traffic": None, "flops_per_obs": flops,
+                                   "kernel": "qs::policy_kernel", "kernel_ms": ms / K,
+                                   "peak_source": "measured bf16 sustained" if peaks else "fallback"}
+            print(json.dumps(out))
+        env.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- end to end through the C ABI with HOST (pinned) buffers: H2D actions, step, D2H obs/reward/done per step
     lib = env._lib

@@ -166,6 +166,35 @@ uint64_t qs_launch_count(const qs_env *env);
  * (5, 6 are -1 for INDI).  Any out pointer may be NULL. */
 int qs_get_state_layout(qs_env *env, void **base, int *block_bytes, int *offsets7);
 
+/* ---- on-device policy ----------------------------------------------------------- */
+/* The trained controller the reference evaluates through SB3 (`model.predict(env.states)`, `3D quad race.ipynb:803`)
+ * or through its generated C (`c_code/neural_network.c:397-430`, noise + clip `c_code/nn_controller.c:158-176`):
+ *   mean = W_out . relu(W_h ... relu(W_1 . obs + b_1) ...) + b_out ;  action = clip(mean + std * N(0,1), -1, 1).
+ * Evaluated on the tensor cores (tcgen05, BF16 operands, FP32 accumulation in TMEM), observations and actions stay
+ * on the device.  in_dim 1..63, 1..4 hidden layers of width <= 127, out_dim <= 4. */
+typedef struct qs_policy qs_policy; /* opaque */
+int qs_policy_create(qs_policy **out, int in_dim, int n_hidden, int hidden_dim, int out_dim, int device, void *stream);
+int qs_policy_destroy(qs_policy *policy);
+const char *qs_policy_last_error(const qs_policy *policy); /* NULL: error of the last failed qs_policy_create */
+int qs_policy_set_stream(qs_policy *policy, void *stream);
+/* layer 0..n_hidden (the last is the output layer); W row-major [out][in] and b [out] as torch / the generated C
+ * store them (`c_code/neural_network.c:5-395`), host float32 */
+int qs_policy_set_layer(qs_policy *policy, int layer, const float *W, const float *b);
+int qs_policy_set_std(qs_policy *policy, const float *std);          /* exp(log_std), `c_code/nn_controller.c:7-12` */
+int qs_policy_seed(qs_policy *policy, uint64_t seed);                /* exploration noise: Philox keyed by (seed, global env, launch) */
+int qs_policy_set_env_offset(qs_policy *policy, int64_t global_index_of_env0);
+/* actions_dev (n,4) f32 <- policy(obs_dev (n,in_dim) f32); mean_dev (n,4) f32 receives the pre-noise output when not
+ * NULL; deterministic != 0 skips the noise (`nn_controller.c:5`).  Asynchronous on the policy's stream. */
+int qs_policy_forward(qs_policy *policy, const float *obs_dev, int64_t n, float *actions_dev, float *mean_dev,
+                      int deterministic);
+uint64_t qs_policy_launch_count(const qs_policy *policy);
+/* collect_rollouts without the host (SB3's loop behind `model.learn`, `3D quad race.ipynb:820`): for t < steps
+ *   act_buf[t] = policy(obs_buf[t]);  obs_buf[t+1], rew_buf[t], done_buf[t] = step(act_buf[t])   (fused device reset)
+ * obs_buf (steps+1, N, obs_len) f32 with obs_buf[0] = current observations, act_buf (steps, N, 4) f32,
+ * rew_buf (steps, N) f32, done_buf (steps, N) u8 -- all device pointers.  Asynchronous on the env's stream. */
+int qs_rollout(qs_env *env, qs_policy *policy, int steps, float *obs_buf, float *act_buf, float *rew_buf,
+               uint8_t *done_buf, int deterministic);
+
 #ifdef __cplusplus
 }
 #endif

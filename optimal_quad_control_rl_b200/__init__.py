@@ -8,4 +8,7 @@ def __getattr__(name):  # envs needs torch + the CUDA library: import lazily so 
     if name in ("Quadcopter3DGates", "Quadcopter3DGatesINDI", "load_residual_weights"):
         from . import envs
         return getattr(envs, name)
+    if name == "MlpPolicy":
+        from . import policy
+        return policy.MlpPolicy
     raise AttributeError(name)

@@ -59,6 +59,17 @@ SIGNATURES = {
     "qs_algorithmic_bytes_per_env_step": (C.c_int, [C.c_int, C.c_int]),
     "qs_launch_count": (C.c_uint64, [_vp]),
     "qs_get_state_layout": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "qs_policy_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "qs_policy_destroy": (C.c_int, [_vp]),
+    "qs_policy_last_error": (C.c_char_p, [_vp]),
+    "qs_policy_set_stream": (C.c_int, [_vp, _vp]),
+    "qs_policy_set_layer": (C.c_int, [_vp, C.c_int, _fp, _fp]),
+    "qs_policy_set_std": (C.c_int, [_vp, _fp]),
+    "qs_policy_seed": (C.c_int, [_vp, C.c_uint64]),
+    "qs_policy_set_env_offset": (C.c_int, [_vp, C.c_int64]),
+    "qs_policy_forward": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, C.c_int]),
+    "qs_policy_launch_count": (C.c_uint64, [_vp]),
+    "qs_rollout": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int]),
 }
 
 _LIB = None

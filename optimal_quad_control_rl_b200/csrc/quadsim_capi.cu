@@ -2,6 +2,7 @@
 // Owns the device planes, builds the kernel parameter block, launches the sm_100a kernels of quadsim_kernels.cuh.
 // No torch, no Python: plain pointers and sizes only.
 #include "quadsim_kernels.cuh"
+#include "quadsim_policy.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -44,6 +45,9 @@ struct qs_env {
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
     uint64_t launches = 0;
+    cudaStream_t copy_a = nullptr, copy_b = nullptr;  // host-buffer pipeline: upload+kernel / download
+    cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr;
+    int host_chunks = 4;   // measured on B200 + PCIe Gen5: 1 -> 4.67e8, 4 -> 5.13e8 env-steps/s at N = 2^20
     int stages = 2, step_grid = 0;  // pipeline depth and persistent grid of the step kernel
     bool pdl = true;                // programmatic dependent launch of consecutive steps
     size_t step_smem = 0;
@@ -238,6 +242,11 @@ int qs_destroy(qs_env *e) {
     Planes &s = e->planes;
     cudaFree(s.base); cudaFree(e->epoch_dev); cudaFree(e->track_dev); cudaFree(e->stats_dev); cudaFree(e->scratch);
     cudaFree(e->h_act); cudaFree(e->h_obs); cudaFree(e->h_rew); cudaFree(e->h_done); cudaFree(e->h_flags);
+    if (e->copy_a) cudaStreamDestroy(e->copy_a);
+    if (e->copy_b) cudaStreamDestroy(e->copy_b);
+    if (e->ev_in) cudaEventDestroy(e->ev_in);
+    if (e->ev_k) cudaEventDestroy(e->ev_k);
+    if (e->ev_out) cudaEventDestroy(e->ev_out);
     delete e;
     return QS_OK;
 }
@@ -434,34 +443,49 @@ static int launch_observe(qs_env *e, float *obs_dev, int reset_all, const char *
 int qs_observe(qs_env *e, float *obs_dev) { QS_CHECK_ENV(e); return launch_observe(e, obs_dev, 0, "qs_observe"); }
 int qs_reset_all(qs_env *e, float *obs_dev) { QS_CHECK_ENV(e); return launch_observe(e, obs_dev, 1, "qs_reset_all"); }
 
+static int check_step_args(qs_env *e, const void *act, const void *obs, const void *rew, const void *done, int mode,
+                           int reset_source, const char *who) {
+    if (!act || !rew || !done) { e->err = std::string(who) + ": NULL buffer"; return QS_ERR_ARG; }
+    if (mode < QS_MODE_NORMAL || mode > QS_MODE_PAUSE) { e->err = std::string(who) + ": bad mode"; return QS_ERR_ARG; }
+    if (reset_source != QS_RESET_DEVICE && reset_source != QS_RESET_HOST) { e->err = std::string(who) + ": bad reset_source"; return QS_ERR_ARG; }
+    if (mode != QS_MODE_PAUSE && !obs) { e->err = std::string(who) + ": obs buffer is NULL"; return QS_ERR_ARG; }
+    return QS_OK;
+}
+
+// one launch of the step kernel over the 128-env tiles [t0, t1) on `stream`; e->P already holds the buffers
+static int launch_step(qs_env *e, long long t0, long long t1, int advance_epoch, cudaStream_t stream, bool pdl) {
+    StepParams &P = e->P;
+    P.tile_begin = t0; P.tile_end = t1; P.advance_epoch = advance_epoch;
+    const long long tiles = t1 - t0;
+    // programmatic dependent launch: this grid's prologue may overlap the tail of the previous kernel on the
+    // stream; the kernel itself waits (griddepcontrol.wait) before it touches simulator state
+    void *args[] = {&P};
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(tiles < e->step_grid ? tiles : e->step_grid));
+    cfg.blockDim = dim3(qs::kStepThreads);
+    cfg.dynamicSmemBytes = e->step_smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    QS_CUDA(e, cudaLaunchKernelExC(&cfg, step_function(e), args));
+    e->launches++;
+    return QS_OK;
+}
+
 int qs_step(qs_env *e, const float *actions_dev, float *obs_dev, float *rew_dev, uint8_t *done_dev, uint8_t *flags_dev,
             int mode, int reset_source) {
     QS_CHECK_ENV(e);
-    if (!actions_dev || !rew_dev || !done_dev) return fail(e, QS_ERR_ARG, "qs_step: NULL buffer");
-    if (mode < QS_MODE_NORMAL || mode > QS_MODE_PAUSE) return fail(e, QS_ERR_ARG, "qs_step: bad mode");
-    if (reset_source != QS_RESET_DEVICE && reset_source != QS_RESET_HOST) return fail(e, QS_ERR_ARG, "qs_step: bad reset_source");
-    if (mode != QS_MODE_PAUSE && !obs_dev) return fail(e, QS_ERR_ARG, "qs_step: obs_dev is NULL");
+    if (int r = check_step_args(e, actions_dev, obs_dev, rew_dev, done_dev, mode, reset_source, "qs_step")) return r;
     if ((uintptr_t)actions_dev & 15) return fail(e, QS_ERR_ARG, "qs_step: actions_dev must be 16-byte aligned");
     if (int r = prep_launch(e, "qs_step")) return r;
     StepParams &P = e->P;
     P.actions = reinterpret_cast<const float4 *>(actions_dev);
     P.obs = obs_dev; P.rew = rew_dev; P.done = done_dev; P.flags = flags_dev;
     P.mode = mode; P.reset_source = reset_source;
-    // programmatic dependent launch: this grid's prologue may overlap the tail of the previous kernel on the
-    // stream; the kernel itself waits (griddepcontrol.wait) before it touches simulator state
-    void *args[] = {&P};
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)e->step_grid);
-    cfg.blockDim = dim3(qs::kStepThreads);
-    cfg.dynamicSmemBytes = e->step_smem;
-    cfg.stream = e->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = e->pdl ? 1 : 0;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    QS_CUDA(e, cudaLaunchKernelExC(&cfg, step_function(e), args));
-    e->launches++;
+    if (int r = launch_step(e, 0, (e->n + qs::kBlock - 1) / qs::kBlock, 1, e->stream, e->pdl)) return r;
     QS_CUDA(e, cudaGetLastError());
     return QS_OK;
 }
@@ -505,23 +529,55 @@ static int ensure_io(qs_env *e) {
     QS_CUDA(e, cudaMalloc(&e->h_rew, n * 4));
     QS_CUDA(e, cudaMalloc(&e->h_done, n));
     QS_CUDA(e, cudaMalloc(&e->h_flags, n));
+    QS_CUDA(e, cudaStreamCreateWithFlags(&e->copy_a, cudaStreamNonBlocking));
+    QS_CUDA(e, cudaStreamCreateWithFlags(&e->copy_b, cudaStreamNonBlocking));
+    QS_CUDA(e, cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
+    QS_CUDA(e, cudaEventCreateWithFlags(&e->ev_k, cudaEventDisableTiming));
+    QS_CUDA(e, cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
+    if (const char *cv = getenv("QS_HOST_CHUNKS")) { int v = atoi(cv); if (v >= 1 && v <= 64) e->host_chunks = v; }
     return QS_OK;
 }
 
+// One step with HOST buffers, software-pipelined over chunks of envs so that PCIe runs in both directions at once:
+// stream A carries  H2D(actions c) -> step kernel(chunk c)  and stream B the D2H of chunk c's outputs, so the
+// upload of chunk c+1 overlaps the download of chunk c.  All chunk launches read the same RNG epoch; the last one
+// advances it, so the result is bit-identical to one qs_step over device buffers.
 int qs_step_host(qs_env *e, const float *act, float *obs, float *rew, uint8_t *done, uint8_t *flags, int mode,
                  int reset_source) {
     QS_CHECK_ENV(e);
-    if (!act || !rew || !done) return fail(e, QS_ERR_ARG, "qs_step_host: NULL buffer");
+    if (int r = check_step_args(e, act, obs, rew, done, mode, reset_source, "qs_step_host")) return r;
     if (int r = ensure_io(e)) return r;
-    const size_t n = (size_t)e->n;
-    QS_CUDA(e, cudaMemcpyAsync(e->h_act, act, n * 16, cudaMemcpyHostToDevice, e->stream));
-    if (int r = qs_step(e, e->h_act, e->h_obs, e->h_rew, e->h_done, flags ? e->h_flags : nullptr, mode, reset_source)) return r;
-    if (obs && mode != QS_MODE_PAUSE)
-        QS_CUDA(e, cudaMemcpyAsync(obs, e->h_obs, n * e->obs_len * 4, cudaMemcpyDeviceToHost, e->stream));
-    QS_CUDA(e, cudaMemcpyAsync(rew, e->h_rew, n * 4, cudaMemcpyDeviceToHost, e->stream));
-    QS_CUDA(e, cudaMemcpyAsync(done, e->h_done, n, cudaMemcpyDeviceToHost, e->stream));
-    if (flags) QS_CUDA(e, cudaMemcpyAsync(flags, e->h_flags, n, cudaMemcpyDeviceToHost, e->stream));
-    QS_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (int r = prep_launch(e, "qs_step_host")) return r;
+    StepParams &P = e->P;
+    P.actions = reinterpret_cast<const float4 *>(e->h_act);
+    P.obs = e->h_obs; P.rew = e->h_rew; P.done = e->h_done; P.flags = flags ? e->h_flags : nullptr;
+    P.mode = mode; P.reset_source = reset_source;
+    const long long tiles = (e->n + qs::kBlock - 1) / qs::kBlock;
+    long long per = (tiles + e->host_chunks - 1) / e->host_chunks;
+    if (per < 256) per = tiles < 256 ? tiles : 256;  // >= 32768 envs per chunk: below that the copies are latency-bound
+    const bool want_obs = obs && mode != QS_MODE_PAUSE;
+    QS_CUDA(e, cudaEventRecord(e->ev_in, e->stream));
+    QS_CUDA(e, cudaStreamWaitEvent(e->copy_a, e->ev_in, 0));
+    QS_CUDA(e, cudaStreamWaitEvent(e->copy_b, e->ev_in, 0));
+    for (long long t0 = 0; t0 < tiles; t0 += per) {
+        const long long t1 = t0 + per < tiles ? t0 + per : tiles;
+        const size_t first = (size_t)t0 * qs::kBlock;
+        const size_t cnt = (size_t)((t1 * qs::kBlock < e->n ? t1 * qs::kBlock : e->n)) - first;
+        QS_CUDA(e, cudaMemcpyAsync(e->h_act + first * 4, act + first * 4, cnt * 16, cudaMemcpyHostToDevice, e->copy_a));
+        if (int r = launch_step(e, t0, t1, t1 == tiles, e->copy_a, false)) return r;
+        QS_CUDA(e, cudaEventRecord(e->ev_k, e->copy_a));
+        QS_CUDA(e, cudaStreamWaitEvent(e->copy_b, e->ev_k, 0));
+        if (want_obs)
+            QS_CUDA(e, cudaMemcpyAsync(obs + first * e->obs_len, e->h_obs + first * e->obs_len, cnt * e->obs_len * 4,
+                                       cudaMemcpyDeviceToHost, e->copy_b));
+        QS_CUDA(e, cudaMemcpyAsync(rew + first, e->h_rew + first, cnt * 4, cudaMemcpyDeviceToHost, e->copy_b));
+        QS_CUDA(e, cudaMemcpyAsync(done + first, e->h_done + first, cnt, cudaMemcpyDeviceToHost, e->copy_b));
+        if (flags) QS_CUDA(e, cudaMemcpyAsync(flags + first, e->h_flags + first, cnt, cudaMemcpyDeviceToHost, e->copy_b));
+    }
+    QS_CUDA(e, cudaGetLastError());
+    QS_CUDA(e, cudaEventRecord(e->ev_out, e->copy_b));
+    QS_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_out, 0));  // later work on the handle's stream is ordered after us
+    QS_CUDA(e, cudaEventSynchronize(e->ev_out));
     return QS_OK;
 }
 
@@ -541,5 +597,210 @@ void *qs_host_alloc(size_t bytes) {
     return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
 }
 void qs_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+
+// ================================================================================================ on-device policy
+// the trained controller MLP evaluated next to the simulator (quadsim_policy.cuh).
+struct qs_policy {
+    int device = 0, in_dim = 0, n_hidden = 0, hidden = 0, out_dim = 0, k1 = 0, grid = 0, groups = 4;
+    cudaStream_t stream = nullptr;
+    std::vector<std::vector<float>> W, b;  // host copies, torch layout [out][in]
+    std::vector<bool> have;
+    unsigned char *w_dev = nullptr;
+    unsigned long long *epoch_dev = nullptr;
+    bool dirty = true, pdl = true;
+    uint64_t seed = 0, launches = 0;
+    int64_t env_offset = 0;
+    float std[4] = {0, 0, 0, 0};
+    size_t smem = 0;
+    std::string err;
+};
+
+static std::string g_policy_create_error;
+#define QS_PCHECK(p) \
+    if (!(p)) return QS_ERR_ARG
+static int pfail(qs_policy *p, int code, const char *msg) {
+    if (p) p->err = msg; else g_policy_create_error = msg;
+    return code;
+}
+
+static uint16_t bf16_rne(float f) {  // round-to-nearest-even, what cvt.rn.bf16.f32 does
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);  // inf / nan
+    return (uint16_t)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);
+}
+
+// Weights -> BF16 in the canonical K-major UMMA layout: element (n, k) of a matrix with `rows` (padded) output rows
+// lives in K-slab k/8 at byte (k/8)*rows*16 + n*16 + (k%8)*2.  Biases are folded in: the column that multiplies the
+// constant-1 input (in_dim for layer 1, unit 127 afterwards) holds the bias, and row 127 of every hidden layer
+// reproduces the constant.
+static void pack_policy_weights(const qs_policy *p, std::vector<unsigned char> &blob) {
+    blob.assign(qs::policy_weight_bytes(p->k1, p->n_hidden), 0);
+    size_t off = 0;
+    for (int l = 0; l <= p->n_hidden; ++l) {
+        const bool last = l == p->n_hidden;
+        const int rows = last ? qs::kPolOut : qs::kPolHidden, kk = l == 0 ? p->k1 : qs::kPolHidden;
+        const int n_out = last ? p->out_dim : p->hidden, n_in = l == 0 ? p->in_dim : p->hidden;
+        const int ones_k = l == 0 ? p->in_dim : qs::kPolOnes;
+        auto put = [&](int n, int k, float v) {
+            const uint16_t h = bf16_rne(v);
+            memcpy(&blob[off + (size_t)(k / 8) * rows * 16 + (size_t)n * 16 + (size_t)(k % 8) * 2], &h, 2);
+        };
+        for (int n = 0; n < n_out; ++n) {
+            for (int k = 0; k < n_in; ++k) put(n, k, p->W[l][(size_t)n * n_in + k]);
+            put(n, ones_k, p->b[l][n]);
+        }
+        if (!last) put(qs::kPolOnes, ones_k, 1.0f);
+        off += (size_t)(kk / 8) * rows * 16;
+    }
+}
+
+const char *qs_policy_last_error(const qs_policy *p) { return p ? p->err.c_str() : g_policy_create_error.c_str(); }
+uint64_t qs_policy_launch_count(const qs_policy *p) { return p ? p->launches : 0; }
+
+int qs_policy_create(qs_policy **out, int in_dim, int n_hidden, int hidden_dim, int out_dim, int device, void *stream) {
+    if (!out) return pfail(nullptr, QS_ERR_ARG, "qs_policy_create: out is NULL");
+    *out = nullptr;
+    if (in_dim < 1 || in_dim > 63) return pfail(nullptr, QS_ERR_ARG, "qs_policy_create: in_dim must be 1..63");
+    if (n_hidden < 1 || n_hidden > 4) return pfail(nullptr, QS_ERR_ARG, "qs_policy_create: 1..4 hidden layers");
+    if (hidden_dim < 1 || hidden_dim > qs::kPolOnes) return pfail(nullptr, QS_ERR_ARG, "qs_policy_create: hidden_dim must be 1..127");
+    if (out_dim < 1 || out_dim > 4) return pfail(nullptr, QS_ERR_ARG, "qs_policy_create: out_dim must be 1..4");
+    qs_policy *p = new (std::nothrow) qs_policy();
+    if (!p) return pfail(nullptr, QS_ERR_NOMEM, "qs_policy_create: out of host memory");
+    p->device = device; p->in_dim = in_dim; p->n_hidden = n_hidden; p->hidden = hidden_dim; p->out_dim = out_dim;
+    p->k1 = (in_dim + 1 + 15) / 16 * 16;
+    p->stream = (cudaStream_t)stream;
+    p->W.resize(n_hidden + 1); p->b.resize(n_hidden + 1); p->have.assign(n_hidden + 1, false);
+    auto bail = [&](cudaError_t c, const char *what) {
+        g_policy_create_error = std::string(what) + ": " + cudaGetErrorString(c);
+        qs_policy_destroy(p);
+        return (int)QS_ERR_CUDA;
+    };
+    cudaError_t c;
+    if ((c = cudaSetDevice(device)) != cudaSuccess) return bail(c, "cudaSetDevice");
+    int sms = 0, smem_max = 0;
+    if ((c = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return bail(c, "cudaDeviceGetAttribute");
+    if ((c = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)) != cudaSuccess) return bail(c, "cudaDeviceGetAttribute");
+    // one CTA per SM; as many 128-row tile groups (each 32 KB of A operand + 128 TMEM columns) as fit beside the weights
+    if (const char *gv = getenv("QS_POLICY_GROUPS")) { int v = atoi(gv); if (v >= 1 && v <= 4) p->groups = v; }
+    while (p->groups > 1 && qs::policy_smem_bytes(p->k1, n_hidden, p->groups) > (size_t)smem_max) p->groups--;
+    p->smem = qs::policy_smem_bytes(p->k1, n_hidden, p->groups);
+    if (p->smem > (size_t)smem_max) { g_policy_create_error = "policy weights do not fit in shared memory"; qs_policy_destroy(p); return QS_ERR_ARG; }
+    if ((c = cudaMalloc(&p->w_dev, qs::policy_weight_bytes(p->k1, n_hidden))) != cudaSuccess) return bail(c, "cudaMalloc");
+    if ((c = cudaMalloc(&p->epoch_dev, 16)) != cudaSuccess) return bail(c, "cudaMalloc");
+    if ((c = cudaMemset(p->epoch_dev, 0, 16)) != cudaSuccess) return bail(c, "cudaMemset");
+    if ((c = cudaFuncSetAttribute((const void *)qs::policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem)) != cudaSuccess)
+        return bail(c, "cudaFuncSetAttribute(policy smem)");
+    if (const char *pv = getenv("QS_PDL")) p->pdl = atoi(pv) != 0;
+    p->grid = sms;
+    *out = p;
+    return QS_OK;
+}
+
+int qs_policy_destroy(qs_policy *p) {
+    if (!p) return QS_OK;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream); else cudaDeviceSynchronize();
+    cudaFree(p->w_dev); cudaFree(p->epoch_dev);
+    delete p;
+    return QS_OK;
+}
+
+int qs_policy_set_stream(qs_policy *p, void *stream) { QS_PCHECK(p); p->stream = (cudaStream_t)stream; return QS_OK; }
+int qs_policy_set_env_offset(qs_policy *p, int64_t off) { QS_PCHECK(p); p->env_offset = off; return QS_OK; }
+int qs_policy_seed(qs_policy *p, uint64_t seed) {
+    QS_PCHECK(p);
+    p->seed = seed;
+    if (cudaSetDevice(p->device) != cudaSuccess || cudaMemsetAsync(p->epoch_dev, 0, 16, p->stream) != cudaSuccess)
+        return pfail(p, QS_ERR_CUDA, "qs_policy_seed: CUDA error");
+    return QS_OK;
+}
+
+int qs_policy_set_layer(qs_policy *p, int layer, const float *W, const float *b) {
+    QS_PCHECK(p);
+    if (layer < 0 || layer > p->n_hidden || !W || !b) return pfail(p, QS_ERR_ARG, "qs_policy_set_layer: bad argument");
+    const int n_out = layer == p->n_hidden ? p->out_dim : p->hidden, n_in = layer == 0 ? p->in_dim : p->hidden;
+    p->W[layer].assign(W, W + (size_t)n_out * n_in);
+    p->b[layer].assign(b, b + n_out);
+    p->have[layer] = true;
+    p->dirty = true;
+    return QS_OK;
+}
+
+int qs_policy_set_std(qs_policy *p, const float *std4) {
+    QS_PCHECK(p);
+    if (!std4) return pfail(p, QS_ERR_ARG, "qs_policy_set_std: NULL");
+    for (int k = 0; k < p->out_dim; ++k) p->std[k] = std4[k];
+    return QS_OK;
+}
+
+static int policy_launch(qs_policy *p, const float *obs_dev, int64_t n, float *actions_dev, float *mean_dev, int deterministic,
+                         cudaStream_t stream) {
+    for (int l = 0; l <= p->n_hidden; ++l)
+        if (!p->have[l]) return pfail(p, QS_ERR_STATE, "qs_policy_forward: a layer's weights are not set (qs_policy_set_layer)");
+    if (cudaSetDevice(p->device) != cudaSuccess) return pfail(p, QS_ERR_CUDA, "cudaSetDevice failed");
+    if (p->dirty) {
+        std::vector<unsigned char> blob;
+        pack_policy_weights(p, blob);
+        if (cudaStreamSynchronize(stream) != cudaSuccess || cudaMemcpy(p->w_dev, blob.data(), blob.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+            return pfail(p, QS_ERR_CUDA, "qs_policy_forward: weight upload failed");
+        p->dirty = false;
+    }
+    qs::PolicyParams P{};
+    P.obs = obs_dev; P.actions = actions_dev; P.mean = mean_dev; P.weights = p->w_dev; P.epoch = p->epoch_dev;
+    P.n = n; P.env_offset = p->env_offset; P.seed = p->seed; P.in_dim = p->in_dim; P.k1 = p->k1; P.n_hidden = p->n_hidden;
+    P.out_dim = p->out_dim; P.deterministic = deterministic;
+    P.weight_bytes = qs::policy_weight_bytes(p->k1, p->n_hidden);
+    P.tmem_cols = p->groups <= 1 ? 128u : (p->groups == 2 ? 256u : 512u);
+    for (int k = 0; k < 4; ++k) P.std[k] = p->std[k];
+    const long long tiles = (n + qs::kPolRows - 1) / qs::kPolRows;
+    void *args[] = {&P};
+    cudaLaunchConfig_t cfg{};
+    const long long ctas = (tiles + p->groups - 1) / p->groups;
+    cfg.gridDim = dim3((unsigned)(ctas < p->grid ? ctas : p->grid));
+    cfg.blockDim = dim3((unsigned)(qs::kPolRows * p->groups));
+    cfg.dynamicSmemBytes = p->smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = p->pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t c = cudaLaunchKernelExC(&cfg, (const void *)qs::policy_kernel, args);
+    if (c != cudaSuccess) { p->err = std::string("policy_kernel launch: ") + cudaGetErrorString(c); return QS_ERR_CUDA; }
+    p->launches++;
+    return QS_OK;
+}
+
+int qs_policy_forward(qs_policy *p, const float *obs_dev, int64_t n, float *actions_dev, float *mean_dev, int deterministic) {
+    QS_PCHECK(p);
+    if (!obs_dev || !actions_dev || n <= 0) return pfail(p, QS_ERR_ARG, "qs_policy_forward: bad argument");
+    if (((uintptr_t)actions_dev & 15) || ((uintptr_t)mean_dev & 15)) return pfail(p, QS_ERR_ARG, "qs_policy_forward: outputs must be 16-byte aligned");
+    if ((p->in_dim & 3) == 0 && ((uintptr_t)obs_dev & 15)) return pfail(p, QS_ERR_ARG, "qs_policy_forward: obs_dev must be 16-byte aligned");
+    return policy_launch(p, obs_dev, n, actions_dev, mean_dev, deterministic, p->stream);
+}
+
+// collect_rollouts on the device (SB3 `OnPolicyAlgorithm.collect_rollouts`, called from `3D quad race.ipynb:820`): for
+// t < steps:  actions[t] = policy(obs[t]);  obs[t+1], rewards[t], dones[t] = env.step(actions[t]).  2*steps kernel
+// launches enqueued back to back on the env's stream (PDL-chained), no host round trip.  obs[0] must hold the
+// current observations (qs_reset_all / the previous rollout's obs[steps]).
+int qs_rollout(qs_env *e, qs_policy *p, int steps, float *obs_buf, float *act_buf, float *rew_buf, uint8_t *done_buf,
+               int deterministic) {
+    QS_CHECK_ENV(e);
+    if (!p) return fail(e, QS_ERR_ARG, "qs_rollout: policy is NULL");
+    if (steps < 1 || !obs_buf || !act_buf || !rew_buf || !done_buf) return fail(e, QS_ERR_ARG, "qs_rollout: bad argument");
+    if (p->in_dim != e->obs_len) return fail(e, QS_ERR_ARG, "qs_rollout: policy input width != observation width");
+    if (p->out_dim != 4) return fail(e, QS_ERR_ARG, "qs_rollout: the env takes 4 actions");
+    if (p->device != e->device) return fail(e, QS_ERR_ARG, "qs_rollout: env and policy live on different devices");
+    const size_t n = (size_t)e->n;
+    for (int t = 0; t < steps; ++t) {
+        float *obs_t = obs_buf + (size_t)t * n * e->obs_len, *act_t = act_buf + (size_t)t * n * 4;
+        if (int r = policy_launch(p, obs_t, e->n, act_t, nullptr, deterministic, e->stream)) { e->err = p->err; return r; }
+        if (int r = qs_step(e, act_t, obs_t + n * e->obs_len, rew_buf + (size_t)t * n, done_buf + (size_t)t * n, nullptr,
+                            QS_MODE_NORMAL, QS_RESET_DEVICE)) return r;
+    }
+    return QS_OK;
+}
 
 }  // extern "C"

@@ -70,6 +70,9 @@ struct StepParams {
     Stats *stats;        // one slot per CTA of the step kernel (or NULL)
     long long n;
     long long env_offset;
+    long long tile_begin, tile_end;  // 128-env tiles [begin, end) this launch steps (the whole env range, or one
+                                     // chunk of the host-buffer pipeline); advance_epoch marks a step's LAST launch
+    int advance_epoch;
     unsigned long long seed;
     // Time half of the RNG key: number of step / reset launches so far.  It lives in DEVICE memory (epoch[0]) so that
     // a CUDA graph replaying the same launch draws fresh values; the last CTA of a launch to finish (epoch[1] counts
@@ -597,7 +600,8 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
     unsigned char *stages = smem_raw + kBarBytes + warp * (kStages * S::BYTES);          // this warp's ring
     float *s_obs = reinterpret_cast<float *>(smem_raw + kBarBytes + kWarps * kStages * S::BYTES);
     float *s_track = s_obs + kBlock * P.obs_len;
-    const long long n_tiles = (P.n + kBlock - 1) / kBlock;
+    const long long n_tiles = P.tile_end;
+    const long long tile0 = P.tile_begin + blockIdx.x;
 
     if (lane == 0) {
 #pragma unroll
@@ -613,7 +617,7 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) {
-            const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
+            const long long t = tile0 + (long long)s * gridDim.x;
             if (t < n_tiles) issue_warp_tile<V>(P, stages + s * S::BYTES, &full[s], t * kBlock + warp * 32);
         }
     }
@@ -626,7 +630,7 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
     const float *const warp_obs = s_obs + warp * 32 * P.obs_len;
     bool obs_in_flight = false;  // warp-uniform: a bulk store of this warp's observation slice may still be reading it
     int it = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (long long tile = tile0; tile < n_tiles; tile += gridDim.x, ++it) {
         const int stage = it % kStages;
         unsigned char *st = stages + stage * S::BYTES;
         const long long base = tile * kBlock;
@@ -770,7 +774,7 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
     }
     if (lane == 0 && write_obs_tile) bulk_store_wait_read();  // shared memory must outlive the last bulk read
     __syncthreads();  // every warp of the CTA is past its last reset draw
-    if (tid == 0) epoch_arrive(P);
+    if (tid == 0 && P.advance_epoch) epoch_arrive(P);
 
     if (P.stats) {  // warp-shuffle reduction, then ONE plain read-modify-write per CTA on the CTA's own slot:
                     // no atomics (740-1184 CTAs hammering one address cost 1-4 us per launch), summed by qs_get_stats

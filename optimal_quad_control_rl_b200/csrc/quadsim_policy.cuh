@@ -1,0 +1,289 @@
+// quadsim_policy.cuh -- sm_100a device code of the on-device policy forward.
+//
+// What it replaces: the reference evaluates its trained controller -- an MLP obs(20+4*ga) -> 120 -> 120 -> 120 -> 4
+// with ReLU, Gaussian exploration noise and a clip to [-1,1] -- either through SB3 (`model.predict(env.states)`,
+// `3D quad race.ipynb:803`) or through its generated C (`c_code/neural_network.c:397-430` nn_linear / nn_relu /
+// nn_forward; noise + clip `c_code/nn_controller.c:158-176`).  Here the same function runs next to the simulator:
+// observations never leave the GPU and actions are produced where the step kernel reads them.
+//
+// Shape of the computation: per 128-env tile, a chain of small GEMMs  [128 x K] . [K x 128]  (K = 32, 128, 128) and
+// [128 x 128] . [128 x 16] -- 64 kFLOP per env, two orders of magnitude more arithmetic than the env step, so this
+// (and only this) part of the system belongs on the 5th-generation tensor cores:
+//   * operands in shared memory in the canonical no-swizzle K-major UMMA layout (8-row x 16-byte core matrices),
+//     BF16; weights are converted and laid out once on the host and arrive as ONE TMA bulk copy per CTA;
+//   * tcgen05.mma (kind::f16, M=128, N=128|8, K=16) issued by one elected thread, FP32 accumulators in TMEM;
+//   * completion via tcgen05.commit -> mbarrier; epilogue tcgen05.ld 32x32b (thread = row = env), ReLU, BF16
+//     re-pack straight into the A-operand slabs of the next layer (in place);
+//   * biases are folded into the GEMMs: column `in_dim` of the input is the constant 1, weight row 127 of every
+//     hidden layer reproduces it, and the bias sits in the weight column that multiplies it.
+// Numerics: BF16 inputs / weights / activations, FP32 accumulation.  The CPU oracle (test infrastructure) restates exactly this
+// rounding (qo_policy_forward_bf16); the FP32 reference (the repo's own nn_forward) differs by <= ~1e-2 absolute on
+// outputs of magnitude 1, well below the policy's exploration noise (std 0.85-0.90, `nn_controller.c:7-12`).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "quadsim_kernels.cuh"
+
+namespace qs {
+
+constexpr int kPolRows = 128;     // envs per tile = UMMA M
+constexpr int kPolHidden = 128;   // padded hidden width = UMMA N of hidden layers, K of the layers after
+constexpr int kPolOut = 16;       // padded output width = UMMA N of the last layer (M=128 needs N % 16 == 0)
+constexpr int kPolMaxLayers = 5;  // hidden layers + output layer
+constexpr int kPolOnes = kPolHidden - 1;  // hidden unit that carries the constant 1 (bias folding)
+constexpr int kSlab = kPolRows * 16;      // one K-chunk of 8 BF16 for 128 rows: 2 KB
+
+struct PolicyParams {
+    const float *obs;         // (n, in_dim) f32 row-major
+    float *actions;           // (n, 4) f32: clip(mean + std * N(0,1), -1, 1)
+    float *mean;              // (n, 4) f32 network output before noise, or NULL
+    const unsigned char *weights;  // BF16 blob in UMMA layout (pack_policy_weights in quadsim_capi.cu)
+    unsigned long long *epoch;     // [0] forward launches so far (noise key), [1] CTA arrivals
+    long long n, env_offset;
+    unsigned long long seed;
+    int in_dim, k1;           // k1 = K of layer 1 (multiple of 16, > in_dim)
+    int n_hidden;             // hidden layers (1..4)
+    int out_dim;              // <= 4
+    int deterministic;
+    uint32_t weight_bytes;
+    uint32_t tmem_cols;       // accumulator columns to allocate: 128 per tile group, rounded up to a power of two
+    float std[4];
+};
+
+__host__ __device__ constexpr uint32_t policy_w1_bytes(int k1) { return (uint32_t)(k1 / 8) * kPolHidden * 16; }
+__host__ __device__ constexpr uint32_t policy_wh_bytes() { return (kPolHidden / 8) * kPolHidden * 16; }   // 32 KB
+__host__ __device__ constexpr uint32_t policy_wo_bytes() { return (kPolHidden / 8) * kPolOut * 16; }      // 4 KB
+__host__ __device__ constexpr uint32_t policy_weight_bytes(int k1, int n_hidden) {
+    return policy_w1_bytes(k1) + (uint32_t)(n_hidden - 1) * policy_wh_bytes() + policy_wo_bytes();
+}
+// dynamic shared memory: [mbarriers + tmem slot : 128 B][A operand, 16 slabs, per tile group][weights]
+__host__ __device__ constexpr size_t policy_smem_bytes(int k1, int n_hidden, int groups) {
+    return 128 + (size_t)groups * (kPolHidden / 8) * kSlab + policy_weight_bytes(k1, n_hidden);
+}
+
+// shared-memory matrix descriptor, canonical K-major layout without swizzle: 8 rows x 16 B core matrices,
+// `lbo` = byte distance between the two K-adjacent core matrices of one MMA, `sbo` = between 8-row groups
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);  // bits 46-47: descriptor version 1 (sm_100)
+}
+// instruction descriptor: D=F32, A=B=BF16, both K-major, dense
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 32 lanes x 32 columns of FP32 accumulators: thread i of the warp receives row (lane base + i), columns c..c+31
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {  // round-to-nearest-even, lo in the low half
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+// One thread issues the K/16 MMAs of a layer: D[128 x N] (+)= A[128 x K] . W[N x K]^T
+__device__ __forceinline__ void issue_layer(uint32_t d_tmem, uint32_t a_smem, uint32_t w_smem, int k, int n_rows,
+                                            uint64_t *bar) {
+    const uint32_t idesc = umma_idesc_bf16(kPolRows, n_rows);
+    const uint32_t w_slab = (uint32_t)n_rows * 16u;
+    for (int j = 0; j < k / 16; ++j) {
+        const uint64_t a = umma_desc(a_smem + (uint32_t)j * 2u * kSlab, kSlab, 128);
+        const uint64_t b = umma_desc(w_smem + (uint32_t)j * 2u * w_slab, w_slab, 128);
+        umma_bf16(d_tmem, a, b, idesc, j > 0);
+    }
+    umma_commit(bar);  // implies tcgen05.fence::before_thread_sync
+}
+
+__device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {  // max(x, 0) fused into the conversion
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void group_barrier(int group) {  // the 128 threads of one tile group
+    asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+}
+
+// Persistent, ONE CTA per SM made of `groups` (<= 4) independent tile groups of 128 threads.  The groups share the
+// weights in shared memory; each owns an A-operand buffer (32 KB), 128 accumulator columns of TMEM, an mbarrier and
+// a named block barrier, and walks its own 128-env tiles: thread r of a group owns row r of the tile (its
+// observation on the way in, TMEM lane r on the way out).  A tile is a strictly serial chain  A -> MMA -> epilogue
+// -> MMA ...  of ~4-5 k cycles of which the tensor pipe is busy ~1.7 k, so four chains in flight per SM are what
+// keeps the tensor cores fed: while one group's epilogue runs on the CUDA cores, the others' MMAs run.
+__global__ void __launch_bounds__(4 * kPolRows, 1) policy_kernel(const __grid_constant__ PolicyParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar_w = reinterpret_cast<uint64_t *>(smem_raw);        // weights landed
+    uint64_t *bar_mma_all = bar_w + 1;                               // [group]: a layer's MMAs completed
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + 64);
+    const int groups = blockDim.x / kPolRows;
+    const int group = threadIdx.x / kPolRows, tid = threadIdx.x % kPolRows, warp = tid >> 5;
+    unsigned char *s_a = smem_raw + 128 + group * ((kPolHidden / 8) * kSlab);
+    unsigned char *s_w = smem_raw + 128 + groups * ((kPolHidden / 8) * kSlab);
+    uint64_t *bar_mma = bar_mma_all + group;
+    const long long n_tiles = (P.n + kPolRows - 1) / kPolRows;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_w, 1);
+        for (int g = 0; g < groups; ++g) mbar_init(bar_mma_all + g, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar_w, P.weight_bytes);
+        bulk_load(s_w, P.weights, P.weight_bytes, bar_w);  // launch constant: may precede the PDL wait
+    }
+    if (threadIdx.x < 32) {  // one warp allocates all accumulator columns (a power of two) and owns the dealloc
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(P.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem = tmem_base + (uint32_t)group * kPolHidden;          // this group's accumulator columns
+    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    pdl_launch_dependents();
+    pdl_wait();  // observations come from the previous kernel on the stream (the env step)
+    mbar_wait(bar_w, 0);
+
+    const uint32_t a_smem = smem_u32(s_a), w_smem = smem_u32(s_w);
+    const unsigned long long epoch = P.deterministic ? 0ull : *reinterpret_cast<const volatile unsigned long long *>(P.epoch);
+    const bool vec = (P.in_dim & 3) == 0;  // observation rows of 16-byte multiples: float4 loads
+    const long long stride = (long long)gridDim.x * groups;
+    uint32_t phase = 0;
+    for (long long tile = (long long)blockIdx.x * groups + group; tile < n_tiles; tile += stride) {
+        const long long env = tile * kPolRows + tid;
+        const bool active = env < P.n;
+        // ---- A operand of layer 1: this thread's observation row, BF16, K-chunk by K-chunk; column in_dim = 1
+        {
+            const float *row = P.obs + env * P.in_dim;
+            for (int c = 0; c < P.k1 / 8; ++c) {
+                float x[8];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int k = c * 8 + q * 4;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (active) {
+                        if (vec) {
+                            if (k < P.in_dim) v = *reinterpret_cast<const float4 *>(row + k);
+                        } else {
+                            if (k + 0 < P.in_dim) v.x = row[k + 0];
+                            if (k + 1 < P.in_dim) v.y = row[k + 1];
+                            if (k + 2 < P.in_dim) v.z = row[k + 2];
+                            if (k + 3 < P.in_dim) v.w = row[k + 3];
+                        }
+                    }
+                    x[q * 4 + 0] = v.x; x[q * 4 + 1] = v.y; x[q * 4 + 2] = v.z; x[q * 4 + 3] = v.w;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (c * 8 + q == P.in_dim) x[q] = 1.0f;  // the constant input that multiplies the folded bias
+                *reinterpret_cast<uint4 *>(s_a + c * kSlab + tid * 16) =
+                    make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+            }
+        }
+        uint32_t w_off = 0;
+        for (int layer = 0; layer <= P.n_hidden; ++layer) {
+            const bool last = layer == P.n_hidden;
+            const int k = layer == 0 ? P.k1 : kPolHidden;
+            // generic-proxy writes of A -> visible to the tensor core's async proxy; TMEM reads of the previous
+            // epilogue ordered before the MMAs that overwrite the accumulator
+            fence_proxy_async();
+            tc_fence_before();
+            group_barrier(group);
+            if (tid == 0) {
+                tc_fence_after();
+                issue_layer(tmem, a_smem, w_smem + w_off, k, last ? kPolOut : kPolHidden, bar_mma);
+            }
+            w_off += layer == 0 ? policy_w1_bytes(P.k1) : policy_wh_bytes();
+            mbar_wait(bar_mma, phase);
+            phase ^= 1u;
+            tc_fence_after();
+            if (!last) {
+                // ---- epilogue: ReLU + BF16 in one conversion, straight into the A slabs of the next layer (the MMAs
+                // that read A are done); two 32-column loads in flight
+#pragma unroll 1
+                for (int c = 0; c < kPolHidden / 64; ++c) {
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(t_lane + (uint32_t)c * 64u, v0);
+                    tmem_ld32(t_lane + (uint32_t)c * 64u + 32u, v1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int h = 0; h < 4; ++h)
+                            w[h] = pack_relu_bf16(__uint_as_float(v0[q * 8 + 2 * h]), __uint_as_float(v0[q * 8 + 2 * h + 1]));
+                        *reinterpret_cast<uint4 *>(s_a + (c * 8 + q) * kSlab + tid * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int h = 0; h < 4; ++h)
+                            w[h] = pack_relu_bf16(__uint_as_float(v1[q * 8 + 2 * h]), __uint_as_float(v1[q * 8 + 2 * h + 1]));
+                        *reinterpret_cast<uint4 *>(s_a + (c * 8 + 4 + q) * kSlab + tid * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            } else {
+                uint32_t v[8];
+                tmem_ld8(t_lane, v);
+                tmem_ld_wait();
+                float a[4] = {__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])};
+                if (active) {
+                    if (P.mean) *reinterpret_cast<float4 *>(P.mean + env * 4) = make_float4(a[0], a[1], a[2], a[3]);
+                    if (!P.deterministic) {  // Box-Muller on one Philox block keyed by (seed, global env, launch epoch)
+                        const unsigned long long g = (unsigned long long)(env + P.env_offset);
+                        const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)epoch,
+                                                                 ((uint32_t)(epoch >> 32) << 3) | 7u),
+                                                      make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
+                        const float u0 = 1.0f - u01(r.x), u1 = u01(r.y), u2 = 1.0f - u01(r.z), u3 = u01(r.w);  // u0,u2 in (0,1]
+                        const float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
+                        float s0, c0, s1, c1;
+                        sincospif(2.0f * u1, &s0, &c0);
+                        sincospif(2.0f * u3, &s1, &c1);
+                        a[0] = fmaf(P.std[0], r0 * c0, a[0]); a[1] = fmaf(P.std[1], r0 * s0, a[1]);
+                        a[2] = fmaf(P.std[2], r1 * c1, a[2]); a[3] = fmaf(P.std[3], r1 * s1, a[3]);
+                    }
+#pragma unroll
+                    for (int k2 = 0; k2 < 4; ++k2) a[k2] = fminf(fmaxf(a[k2], -1.0f), 1.0f);  // `nn_controller.c:171-173`
+                    *reinterpret_cast<float4 *>(P.actions + env * 4) = make_float4(a[0], a[1], a[2], a[3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols) : "memory");
+    if (threadIdx.x == 0 && !P.deterministic) {  // advance the noise epoch once per launch (same protocol as the step kernel)
+        __threadfence();
+        if (atomicAdd(P.epoch + 1, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+            P.epoch[1] = 0;
+            P.epoch[0] = P.epoch[0] + 1;
+        }
+    }
+}
+
+}  // namespace qs

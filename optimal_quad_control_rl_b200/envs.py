@@ -337,6 +337,26 @@ class _QuadGatesBase(_VecEnvBase):
                    L._vp(self._flags_ring[k].data_ptr()), self._mode(), L.RESET_DEVICE)
         return obs_d, self._rew_ring[k], self._done_ring[k], self._flags_ring[k]
 
+    def rollout(self, policy, steps, deterministic=False, buffers=None):
+        """collect_rollouts on the device (SB3's loop behind `model.learn`, `3D quad race.ipynb:820`): ``steps`` x
+        (policy forward -> env step) enqueued back to back, no host round trip.  Returns CUDA tensors
+        ``obs (steps+1, N, D)``, ``actions (steps, N, 4)``, ``rewards (steps, N)``, ``dones (steps, N)`` (uint8);
+        ``obs[0]`` is the observation the rollout started from, ``obs[steps]`` the one the next rollout starts from."""
+        n, d, dev = self.num_envs, self.state_len, self.device
+        self._push_config()
+        self._sync_stream()
+        if buffers is None:
+            buffers = {"obs": torch.empty((steps + 1, n, d), dtype=torch.float32, device=dev),
+                       "actions": torch.empty((steps, n, 4), dtype=torch.float32, device=dev),
+                       "rewards": torch.empty((steps, n), dtype=torch.float32, device=dev),
+                       "dones": torch.empty((steps, n), dtype=torch.uint8, device=dev)}
+            buffers["obs"][0].copy_(self._obs_ring[self._ring])
+        self._call("qs_rollout", policy._h, int(steps), L._vp(buffers["obs"].data_ptr()),
+                   L._vp(buffers["actions"].data_ptr()), L._vp(buffers["rewards"].data_ptr()),
+                   L._vp(buffers["dones"].data_ptr()), int(bool(deterministic)))
+        self._obs_ring[self._ring].copy_(buffers["obs"][steps])
+        return buffers
+
     def enable_stats(self, on=True):
         self._call("qs_enable_stats", int(on))
 

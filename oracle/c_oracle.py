@@ -55,6 +55,8 @@ def lib():
         L = C.CDLL(LIB_PATH)
         pp = C.POINTER(QoParams)
         L.qo_num_threads.restype = C.c_int
+        L.qo_set_num_threads.argtypes = [C.c_int]
+        L.qo_set_num_threads.restype = None
         L.qo_track_tables.argtypes = [C.c_int, _fp, _fp, _fp, _fp]
         L.qo_body_velocity.argtypes = [_fp, C.c_int64, _fp]
         L.qo_residual_mlp.argtypes = [pp, _fp, C.c_int64, _fp, _fp]
@@ -262,3 +264,33 @@ def euler(env: OracleEnv, ws, act, dist=None):
     d = None if dist is None else np.ascontiguousarray(dist, np.float32)
     lib().qo_euler(C.byref(p), _f(ws), _f(act), _f(d), n, _f(out), _f(th), _f(mo))
     return out, th, mo
+
+
+# ------------------------------------------------------------------------------------------------ policy (row f1)
+def policy_forward(weights, biases, obs, bf16=False):
+    """The controller MLP on the CPU: the float32 restatement of `c_code/neural_network.c:397-430`, or (``bf16``)
+    the same network with the B200 tensor-core path's operand rounding."""
+    L = lib()
+    obs = np.ascontiguousarray(obs, np.float32)
+    n, nl = len(obs), len(weights)
+    dims = (C.c_int * (nl + 1))(weights[0].shape[1], *[w.shape[0] for w in weights])
+    ws = [np.ascontiguousarray(w, np.float32) for w in weights]
+    bs = [np.ascontiguousarray(b, np.float32) for b in biases]
+    wp = (_fp * nl)(*[_f(w) for w in ws])
+    bp = (_fp * nl)(*[_f(b) for b in bs])
+    out = np.empty((n, weights[-1].shape[0]), np.float32)
+    fn = L.qo_policy_forward_bf16 if bf16 else L.qo_policy_forward
+    fn.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(_fp), C.POINTER(_fp), _fp, C.c_int64, _fp]
+    fn.restype = None
+    fn(nl, dims, wp, bp, _f(obs), n, _f(out))
+    return out
+
+
+def ref_policy_lib():
+    """The reference's own generated C policy (c_code/neural_network.c + nn_controller.c) compiled into oracle/_ref."""
+    path = os.path.join(HERE, "_ref", "libnn_policy_ref.so")
+    if not os.path.isfile(path):
+        return None
+    L = C.CDLL(path)
+    L.nn_forward.argtypes = [_fp, _fp]
+    return L

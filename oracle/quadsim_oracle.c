@@ -68,6 +68,15 @@ int qo_obs_len(int variant, int gates_ahead) {
     return variant == QO_E2E ? 20 + 4 * gates_ahead : 13 + 4 * gates_ahead;
 }
 
+/* bench.py's CPU legs: use every host thread even when the launcher exported OMP_NUM_THREADS=1 (torchrun does) */
+void qo_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int qo_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
@@ -416,5 +425,63 @@ void qo_apply_reset(const qo_params *p, int64_t n, float *ws, float *dist, int64
         sc[i] = 0;
         tg[i] = 0;
         ++k;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ policy forward
+ * TEST INFRASTRUCTURE.  Restates the reference's generated controller network, `c_code/neural_network.c`:
+ *   nn_linear (`:397-405`): neuron = bias; for j: neuron += input[j] * weights[i*in + j]   (float32, that order)
+ *   nn_relu   (`:407-411`), nn_forward (`:419-430`): Linear-ReLU x n_hidden, then Linear.
+ * W[l] is row-major [out][in].  dims = {in, hidden, ..., hidden, out} (n_layers + 1 entries).
+ * Pinned by tests/test_policy_oracle.py against oracle/_ref/libnn_policy_ref.so (the reference's own C, compiled
+ * where it lies) through tests/golden/policy_k4.npz. */
+void qo_policy_forward(int n_layers, const int *dims, const float *const *W, const float *const *b, const float *obs,
+                       int64_t n, float *out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        float cur[256], nxt[256];
+        for (int k = 0; k < dims[0]; ++k) cur[k] = obs[i * dims[0] + k];
+        for (int l = 0; l < n_layers; ++l) {
+            const int in = dims[l], on = dims[l + 1];
+            for (int o = 0; o < on; ++o) {
+                float acc = b[l][o];
+                for (int k = 0; k < in; ++k) acc += cur[k] * W[l][(size_t)o * in + k];
+                nxt[o] = (l + 1 < n_layers) ? fmaxf(0.0f, acc) : acc;
+            }
+            for (int o = 0; o < on; ++o) cur[o] = nxt[o];
+        }
+        for (int o = 0; o < dims[n_layers]; ++o) out[i * dims[n_layers] + o] = cur[o];
+    }
+}
+
+static float qo_bf16(float f) { /* round-to-nearest-even to bfloat16, returned as float */
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7F800000u) != 0x7F800000u) u += 0x7FFFu + ((u >> 16) & 1u);
+    u &= 0xFFFF0000u;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+/* The same network with the arithmetic of the B200 tensor-core path (quadsim_policy.cuh): inputs, weights, biases and
+ * hidden activations rounded to BF16, products exact, accumulation in (at least) float32 -- done here in double
+ * and rounded once, so that the only difference left against the GPU is the tensor core's own summation order. */
+void qo_policy_forward_bf16(int n_layers, const int *dims, const float *const *W, const float *const *b,
+                            const float *obs, int64_t n, float *out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        float cur[256], nxt[256];
+        for (int k = 0; k < dims[0]; ++k) cur[k] = qo_bf16(obs[i * dims[0] + k]);
+        for (int l = 0; l < n_layers; ++l) {
+            const int in = dims[l], on = dims[l + 1];
+            for (int o = 0; o < on; ++o) {
+                double acc = (double)qo_bf16(b[l][o]);
+                for (int k = 0; k < in; ++k) acc += (double)cur[k] * (double)qo_bf16(W[l][(size_t)o * in + k]);
+                const float a = (float)acc;
+                nxt[o] = (l + 1 < n_layers) ? qo_bf16(fmaxf(0.0f, a)) : a;
+            }
+            for (int o = 0; o < on; ++o) cur[o] = nxt[o];
+        }
+        for (int o = 0; o < dims[n_layers]; ++o) out[i * dims[n_layers] + o] = cur[o];
     }
 }

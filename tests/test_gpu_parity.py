@@ -335,11 +335,12 @@ def test_few_resets_per_warp_use_cooperative_draw_and_match_per_lane_draw(varian
     np.testing.assert_array_equal(outs[0][0][sel], outs[1][0][sel])
 
 
-def test_c_abi_host_step_matches_device_step(tracks):
-    """qs_step_host (HOST buffers in/out) == qs_step on device buffers."""
+@pytest.mark.parametrize("n", [5000, 100003])
+def test_c_abi_host_step_matches_device_step(n, tracks):
+    """qs_step_host (HOST buffers in/out; chunk-pipelined above 32768 envs) == qs_step on device buffers,
+    bit for bit, fused resets included."""
     import ctypes as C
     import optimal_quad_control_rl_b200._lib as L
-    n = 5000
     e1 = make_env("e2e", n, tracks, reset_rng="device", seed=3)
     e2 = make_env("e2e", n, tracks, reset_rng="device", seed=3)
     o1 = e1.reset()
@@ -355,6 +356,18 @@ def test_c_abi_host_step_matches_device_step(tracks):
     np.testing.assert_array_equal(obs, o2)
     np.testing.assert_array_equal(rew, rew2)
     np.testing.assert_array_equal(done, done2.astype(bool))
+    np.testing.assert_array_equal(e1.last_flags, fl2)
+    np.testing.assert_array_equal(e1.world_states, e2.world_states)
+    # a second step: the RNG epoch advanced exactly once in both
+    for e in (e1, e2):
+        e.max_steps = 2
+    e2._push_config()
+    obs, rew, done, _ = e1.step(act)
+    e2._call("qs_step_host", act.ctypes.data_as(L._vp), o2.ctypes.data_as(L._vp), rew2.ctypes.data_as(L._vp),
+             done2.ctypes.data_as(L._vp), fl2.ctypes.data_as(L._vp), L.MODE_NORMAL, L.RESET_DEVICE)
+    assert done.all()
+    np.testing.assert_array_equal(obs, o2)
+    np.testing.assert_array_equal(e1.world_states, e2.world_states)
 
 
 def test_errors_are_reported_not_raised_across_abi(tracks):
