@@ -204,6 +204,14 @@ __global__ void __launch_bounds__(4 * kPolRows, 1) policy_kernel(const __grid_co
                     make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
             }
         }
+        {  // the next tile's observation rows: start them towards L2 now, a whole tile of compute before they are read
+            const long long nenv = env + stride * kPolRows;
+            if (nenv < P.n) {
+                const float *nrow = P.obs + nenv * P.in_dim;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + P.in_dim - 1));
+            }
+        }
         uint32_t w_off = 0;
         for (int layer = 0; layer <= P.n_hidden; ++layer) {
             const bool last = layer == P.n_hidden;
