@@ -39,7 +39,9 @@ def parse():
     ap.add_argument("--cpu-envs", type=int, default=1 << 16, help="bounded CPU sample: envs stepped by the CPU arm")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather-obs", action="store_true", help="add the NCCL all-gather of observations per step")
+    ap.add_argument("--gather-obs", nargs="?", const="nccl", default=None, choices=["nccl", "p2p"],
+                    help="add the all-gather of observations per step: nccl = step kernel writes the send slot, NCCL "
+                         "gathers in place; p2p = the step kernel stores its tiles into every peer's buffer itself")
     ap.add_argument("--workload", default="step", choices=["step", "policy", "rollout"],
                     help="step: the env step alone on resident actions (the headline, default); policy: the on-device "
                          "controller forward alone (tcgen05); rollout: policy forward + env step per step, no host")
@@ -207,8 +209,11 @@ def run_ours(a):
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
     acts = [torch.rand((n, 4), generator=gen, device=dev) * 2 - 1 for _ in range(4)]  # resident, > L2 with obs
     gather = None
-    if a.gather_obs:
+    if a.gather_obs == "nccl" or (a.gather_obs and world == 1):
         gather = Q.ObsAllGather(n * world, env.state_len, dev)
+    elif a.gather_obs == "p2p":
+        gather = Q.ObsPeerGather(n * world, env.state_len, dev)
+        gather.attach(env)
 
     pol = None
     if a.workload != "step":
@@ -368,7 +373,7 @@ def run_ours(a):
                        "gates_ahead": ga, "obs_dim": D, "reset": "fused device Philox", "l2": "inputs > L2: "
                        f"{n * (bpe + 16 * 3) / 1e6:.0f} MB touched per step vs 126 MB L2, no flush",
                        "parallelism": f"env-sharded x{world}, no data-path collective" +
-                                      (" + NCCL obs all-gather" if gather is not None else ""),
+                                      (" + obs all-gather (%s)" % a.gather_obs if gather is not None else ""),
                        "done_rate": st["dones"] / max(1, st["env_steps"]) if not a.no_stats else None,
                        "launch": "cuda-graph x%d" % a.graph if graph is not None else "per-step"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -111,6 +111,12 @@ int qs_set_disturbance_ranges(qs_env *env, const double *ranges12, int ranges_ar
 int qs_set_residual_weights(qs_env *env, const float *thrust289, const float *moment451);
 int qs_seed(qs_env *env, uint64_t seed);                            /* device RNG only; rewinds its launch epoch */
 int qs_set_env_offset(qs_env *env, int64_t global_index_of_env0);   /* shard of a multi-GPU job                  */
+/* Fused observation all-gather for a sharded job whose policy needs every rank's observations (BASELINE config 4):
+ * peer_obs_bases[p] is the base of ANOTHER rank's (total_envs, obs_len) gather buffer, mapped into this process
+ * (CUDA IPC / symmetric memory); every qs_step then stores its observation rows into obs_dev AND, tile by tile over
+ * NVLink, into each peer buffer at row (row_offset + env).  n_peers = 0 switches it off.  The caller synchronises
+ * the ranks (one barrier) before reading a gathered buffer. */
+int qs_set_obs_peers(qs_env *env, int n_peers, void *const *peer_obs_bases, int64_t row_offset);
 int qs_enable_stats(qs_env *env, int on);
 int qs_get_stats(qs_env *env, qs_stats *out, int reset_after_read); /* synchronises                              */
 

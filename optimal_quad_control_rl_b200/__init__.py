@@ -1,7 +1,7 @@
 """quadsim-b200: the quadrotor racing environments of tudelft/optimal_quad_control_RL as sm_100a CUDA kernels
 behind the reference's own ``Quadcopter3DGates(VecEnv)`` interface."""
 from .tracks import rectangle_track, training_disturbance_ranges, zigzag_track  # noqa: F401
-from .sharding import ObsAllGather, shard_range  # noqa: F401
+from .sharding import ObsAllGather, ObsPeerGather, shard_range  # noqa: F401
 
 
 def __getattr__(name):  # envs needs torch + the CUDA library: import lazily so CPU-only tooling can import the package

@@ -314,6 +314,17 @@ int qs_set_residual_weights(qs_env *e, const float *t, const float *m) {
     return QS_OK;
 }
 
+int qs_set_obs_peers(qs_env *e, int n_peers, void *const *peer_obs_bases, int64_t row_offset) {
+    QS_CHECK_ENV(e);
+    if (n_peers < 0 || n_peers > 7 || (n_peers && !peer_obs_bases)) return fail(e, QS_ERR_ARG, "qs_set_obs_peers: 0..7 peers");
+    for (int p = 0; p < 7; ++p) e->P.peer_obs[p] = p < n_peers ? (float *)peer_obs_bases[p] : nullptr;
+    for (int p = 0; p < n_peers; ++p)
+        if (!peer_obs_bases[p] || ((uintptr_t)peer_obs_bases[p] & 15)) return fail(e, QS_ERR_ARG, "qs_set_obs_peers: NULL or misaligned peer buffer");
+    e->P.n_peers = n_peers;
+    e->P.peer_row_offset = row_offset;
+    return QS_OK;
+}
+
 int qs_enable_stats(qs_env *e, int on) { QS_CHECK_ENV(e); e->stats_on = on != 0; return QS_OK; }
 
 int qs_get_stats(qs_env *e, qs_stats *out, int reset) {

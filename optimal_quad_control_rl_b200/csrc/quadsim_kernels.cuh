@@ -63,6 +63,11 @@ struct StepParams {
     Planes s;
     const float4 *actions;
     float *obs;
+    // fused observation all-gather: the same rows are also stored straight into the other ranks' gather buffers
+    // (peer memory over NVLink): peer_obs[p] + (peer_row_offset + env) * obs_len
+    float *peer_obs[7];
+    long long peer_row_offset;
+    int n_peers;
     float *rew;
     uint8_t *done;
     uint8_t *flags;
@@ -758,11 +763,19 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
             if (bulk) {  // the warp's rows are contiguous in the (N,D) output: one TMA bulk store
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0 && bytes) bulk_store(dst, warp_obs, bytes);
+                if (lane == 0 && bytes) {
+                    bulk_store(dst, warp_obs, bytes);
+                    for (int p = 0; p < P.n_peers; ++p)  // NVLink: the tile leaves for every peer while the next one is computed
+                        bulk_store(P.peer_obs[p] + (P.peer_row_offset + base + warp * 32) * P.obs_len, warp_obs, bytes);
+                }
                 obs_in_flight = true;
             } else {
                 __syncwarp();
                 for (int i = lane; i < rows * P.obs_len; i += 32) dst[i] = warp_obs[i];
+                for (int p = 0; p < P.n_peers; ++p) {
+                    float *pd = P.peer_obs[p] + (P.peer_row_offset + base + warp * 32) * P.obs_len;
+                    for (int i = lane; i < rows * P.obs_len; i += 32) pd[i] = warp_obs[i];
+                }
                 __syncwarp();
             }
         }

@@ -357,6 +357,12 @@ class _QuadGatesBase(_VecEnvBase):
         self._obs_ring[self._ring].copy_(buffers["obs"][steps])
         return buffers
 
+    def set_obs_peers(self, peer_ptrs, row_offset):
+        """Fused observation all-gather: also store every step's observations into the other ranks' gather buffers
+        (device pointers of peer memory) at row ``row_offset + env``.  ``peer_ptrs=[]`` switches it off."""
+        arr = (L._vp * max(1, len(peer_ptrs)))(*[L._vp(int(p)) for p in peer_ptrs])
+        self._call("qs_set_obs_peers", len(peer_ptrs), arr, int(row_offset))
+
     def enable_stats(self, on=True):
         self._call("qs_enable_stats", int(on))
 

@@ -45,3 +45,33 @@ class ObsAllGather:
             for w in works:
                 w.wait()
         return self.buf
+
+
+class ObsPeerGather:
+    """The observation all-gather fused INTO the step kernel: the gather buffer lives in symmetric memory
+    (``torch.distributed._symmetric_memory``: every rank's buffer is mapped into every process), each rank's step
+    kernel stores its observation tiles into its own slice of ALL buffers over NVLink while it computes the next
+    tile, and one cross-rank barrier replaces the collective.  Same contents as ``ObsAllGather`` afterwards."""
+
+    def __init__(self, total_envs, obs_len, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.first, self.count = shard_range(total_envs, self.rank, self.world)
+        self.buf = symm_mem.empty((total_envs, obs_len), dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, self.group)
+        self.peer_ptrs = [int(p) for r, p in enumerate(self.handle.buffer_ptrs) if r != self.rank]
+
+    def attach(self, env):
+        """Point ``env``'s step kernel at the peers; its ``obs_out`` must be ``local_slot()``."""
+        env.set_obs_peers(self.peer_ptrs, self.first)
+
+    def local_slot(self):
+        return self.buf[self.first:self.first + self.count]
+
+    def gather(self):
+        """Wait until every rank's step kernel has finished writing: afterwards ``buf`` holds all observations."""
+        self.handle.barrier()
+        return self.buf
