@@ -189,17 +189,23 @@ int qs_policy_set_layer(qs_policy *policy, int layer, const float *W, const floa
 int qs_policy_set_std(qs_policy *policy, const float *std);          /* exp(log_std), `c_code/nn_controller.c:7-12` */
 int qs_policy_seed(qs_policy *policy, uint64_t seed);                /* exploration noise: Philox keyed by (seed, global env, launch) */
 int qs_policy_set_env_offset(qs_policy *policy, int64_t global_index_of_env0);
-/* actions_dev (n,4) f32 <- policy(obs_dev (n,in_dim) f32); mean_dev (n,4) f32 receives the pre-noise output when not
- * NULL; deterministic != 0 skips the noise (`nn_controller.c:5`).  Asynchronous on the policy's stream. */
+/* actions_dev (n,4) f32 <- policy(obs_dev (n,in_dim) f32); mean_dev (n,4) f32 receives the pre-noise output and
+ * raw_dev (n,4) f32 the sampled action before the clip (the value PPO takes the log-probability of) when not NULL;
+ * deterministic != 0 skips the noise (`nn_controller.c:5`).  Asynchronous on the policy's stream. */
 int qs_policy_forward(qs_policy *policy, const float *obs_dev, int64_t n, float *actions_dev, float *mean_dev,
-                      int deterministic);
+                      float *raw_dev, int deterministic);
 uint64_t qs_policy_launch_count(const qs_policy *policy);
 /* collect_rollouts without the host (SB3's loop behind `model.learn`, `3D quad race.ipynb:820`): for t < steps
  *   act_buf[t] = policy(obs_buf[t]);  obs_buf[t+1], rew_buf[t], done_buf[t] = step(act_buf[t])   (fused device reset)
- * obs_buf (steps+1, N, obs_len) f32 with obs_buf[0] = current observations, act_buf (steps, N, 4) f32,
+ * obs_buf (steps+1, N, obs_len) f32 with obs_buf[0] = current observations, act_buf (steps, N, 4) f32 (clipped, what
+ * the env received), raw_buf (steps, N, 4) f32 or NULL (un-clipped samples, what SB3 keeps in its RolloutBuffer),
  * rew_buf (steps, N) f32, done_buf (steps, N) u8 -- all device pointers.  Asynchronous on the env's stream. */
-int qs_rollout(qs_env *env, qs_policy *policy, int steps, float *obs_buf, float *act_buf, float *rew_buf,
+int qs_rollout(qs_env *env, qs_policy *policy, int steps, float *obs_buf, float *act_buf, float *raw_buf, float *rew_buf,
                uint8_t *done_buf, int deterministic);
+/* SB3 `RolloutBuffer.compute_returns_and_advantage` on the device: rew/adv/ret (steps, n) f32, val (steps+1, n) f32
+ * (last row = bootstrap values), done (steps, n) u8.  A_t = delta_t + gamma*lambda*(1-done_t)*A_{t+1}. */
+int qs_gae(const float *rew_dev, const float *val_dev, const uint8_t *done_dev, float *adv_dev, float *ret_dev, int64_t n,
+           int steps, float gamma, float lambda, void *stream);
 
 #ifdef __cplusplus
 }

@@ -8,6 +8,9 @@ def __getattr__(name):  # envs needs torch + the CUDA library: import lazily so 
     if name in ("Quadcopter3DGates", "Quadcopter3DGatesINDI", "load_residual_weights"):
         from . import envs
         return getattr(envs, name)
+    if name == "PPO":
+        from . import ppo
+        return ppo.PPO
     if name == "MlpPolicy":
         from . import policy
         return policy.MlpPolicy

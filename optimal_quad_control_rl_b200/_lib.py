@@ -68,9 +68,10 @@ SIGNATURES = {
     "qs_policy_set_std": (C.c_int, [_vp, _fp]),
     "qs_policy_seed": (C.c_int, [_vp, C.c_uint64]),
     "qs_policy_set_env_offset": (C.c_int, [_vp, C.c_int64]),
-    "qs_policy_forward": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, C.c_int]),
+    "qs_policy_forward": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int]),
     "qs_policy_launch_count": (C.c_uint64, [_vp]),
-    "qs_rollout": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int]),
+    "qs_rollout": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int]),
+    "qs_gae": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_float, C.c_float, _vp]),
 }
 
 _LIB = None

@@ -746,8 +746,8 @@ int qs_policy_set_std(qs_policy *p, const float *std4) {
     return QS_OK;
 }
 
-static int policy_launch(qs_policy *p, const float *obs_dev, int64_t n, float *actions_dev, float *mean_dev, int deterministic,
-                         cudaStream_t stream) {
+static int policy_launch(qs_policy *p, const float *obs_dev, int64_t n, float *actions_dev, float *mean_dev, float *raw_dev,
+                         int deterministic, cudaStream_t stream) {
     for (int l = 0; l <= p->n_hidden; ++l)
         if (!p->have[l]) return pfail(p, QS_ERR_STATE, "qs_policy_forward: a layer's weights are not set (qs_policy_set_layer)");
     if (cudaSetDevice(p->device) != cudaSuccess) return pfail(p, QS_ERR_CUDA, "cudaSetDevice failed");
@@ -759,7 +759,7 @@ static int policy_launch(qs_policy *p, const float *obs_dev, int64_t n, float *a
         p->dirty = false;
     }
     qs::PolicyParams P{};
-    P.obs = obs_dev; P.actions = actions_dev; P.mean = mean_dev; P.weights = p->w_dev; P.epoch = p->epoch_dev;
+    P.obs = obs_dev; P.actions = actions_dev; P.mean = mean_dev; P.raw = raw_dev; P.weights = p->w_dev; P.epoch = p->epoch_dev;
     P.n = n; P.env_offset = p->env_offset; P.seed = p->seed; P.in_dim = p->in_dim; P.k1 = p->k1; P.n_hidden = p->n_hidden;
     P.out_dim = p->out_dim; P.deterministic = deterministic;
     P.weight_bytes = qs::policy_weight_bytes(p->k1, p->n_hidden);
@@ -784,20 +784,22 @@ static int policy_launch(qs_policy *p, const float *obs_dev, int64_t n, float *a
     return QS_OK;
 }
 
-int qs_policy_forward(qs_policy *p, const float *obs_dev, int64_t n, float *actions_dev, float *mean_dev, int deterministic) {
+int qs_policy_forward(qs_policy *p, const float *obs_dev, int64_t n, float *actions_dev, float *mean_dev, float *raw_dev,
+                      int deterministic) {
     QS_PCHECK(p);
     if (!obs_dev || !actions_dev || n <= 0) return pfail(p, QS_ERR_ARG, "qs_policy_forward: bad argument");
-    if (((uintptr_t)actions_dev & 15) || ((uintptr_t)mean_dev & 15)) return pfail(p, QS_ERR_ARG, "qs_policy_forward: outputs must be 16-byte aligned");
+    if (((uintptr_t)actions_dev & 15) || ((uintptr_t)mean_dev & 15) || ((uintptr_t)raw_dev & 15))
+        return pfail(p, QS_ERR_ARG, "qs_policy_forward: outputs must be 16-byte aligned");
     if ((p->in_dim & 3) == 0 && ((uintptr_t)obs_dev & 15)) return pfail(p, QS_ERR_ARG, "qs_policy_forward: obs_dev must be 16-byte aligned");
-    return policy_launch(p, obs_dev, n, actions_dev, mean_dev, deterministic, p->stream);
+    return policy_launch(p, obs_dev, n, actions_dev, mean_dev, raw_dev, deterministic, p->stream);
 }
 
 // collect_rollouts on the device (SB3 `OnPolicyAlgorithm.collect_rollouts`, called from `3D quad race.ipynb:820`): for
 // t < steps:  actions[t] = policy(obs[t]);  obs[t+1], rewards[t], dones[t] = env.step(actions[t]).  2*steps kernel
 // launches enqueued back to back on the env's stream (PDL-chained), no host round trip.  obs[0] must hold the
 // current observations (qs_reset_all / the previous rollout's obs[steps]).
-int qs_rollout(qs_env *e, qs_policy *p, int steps, float *obs_buf, float *act_buf, float *rew_buf, uint8_t *done_buf,
-               int deterministic) {
+int qs_rollout(qs_env *e, qs_policy *p, int steps, float *obs_buf, float *act_buf, float *raw_buf, float *rew_buf,
+               uint8_t *done_buf, int deterministic) {
     QS_CHECK_ENV(e);
     if (!p) return fail(e, QS_ERR_ARG, "qs_rollout: policy is NULL");
     if (steps < 1 || !obs_buf || !act_buf || !rew_buf || !done_buf) return fail(e, QS_ERR_ARG, "qs_rollout: bad argument");
@@ -807,11 +809,22 @@ int qs_rollout(qs_env *e, qs_policy *p, int steps, float *obs_buf, float *act_bu
     const size_t n = (size_t)e->n;
     for (int t = 0; t < steps; ++t) {
         float *obs_t = obs_buf + (size_t)t * n * e->obs_len, *act_t = act_buf + (size_t)t * n * 4;
-        if (int r = policy_launch(p, obs_t, e->n, act_t, nullptr, deterministic, e->stream)) { e->err = p->err; return r; }
+        float *raw_t = raw_buf ? raw_buf + (size_t)t * n * 4 : nullptr;
+        if (int r = policy_launch(p, obs_t, e->n, act_t, nullptr, raw_t, deterministic, e->stream)) { e->err = p->err; return r; }
         if (int r = qs_step(e, act_t, obs_t + n * e->obs_len, rew_buf + (size_t)t * n, done_buf + (size_t)t * n, nullptr,
                             QS_MODE_NORMAL, QS_RESET_DEVICE)) return r;
     }
     return QS_OK;
+}
+
+// compute_returns_and_advantage on the device (see gae_kernel).  rew/adv/ret (steps, n) f32, val (steps+1, n) f32,
+// done (steps, n) u8; asynchronous on `stream`.
+int qs_gae(const float *rew_dev, const float *val_dev, const uint8_t *done_dev, float *adv_dev, float *ret_dev, int64_t n,
+           int steps, float gamma, float lambda, void *stream) {
+    if (!rew_dev || !val_dev || !done_dev || !adv_dev || !ret_dev || n <= 0 || steps <= 0) return QS_ERR_ARG;
+    qs::gae_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rew_dev, val_dev, done_dev, adv_dev, ret_dev, n,
+                                                                                 steps, gamma, lambda);
+    return cudaGetLastError() == cudaSuccess ? QS_OK : QS_ERR_CUDA;
 }
 
 }  // extern "C"

@@ -37,6 +37,7 @@ struct PolicyParams {
     const float *obs;         // (n, in_dim) f32 row-major
     float *actions;           // (n, 4) f32: clip(mean + std * N(0,1), -1, 1)
     float *mean;              // (n, 4) f32 network output before noise, or NULL
+    float *raw;               // (n, 4) f32 sampled action BEFORE the clip (what PPO's log-prob is taken of), or NULL
     const unsigned char *weights;  // BF16 blob in UMMA layout (pack_policy_weights in quadsim_capi.cu)
     unsigned long long *epoch;     // [0] forward launches so far (noise key), [1] CTA arrivals
     long long n, env_offset;
@@ -275,6 +276,7 @@ __global__ void __launch_bounds__(4 * kPolRows, 1) policy_kernel(const __grid_co
                         a[0] = fmaf(P.std[0], r0 * c0, a[0]); a[1] = fmaf(P.std[1], r0 * s0, a[1]);
                         a[2] = fmaf(P.std[2], r1 * c1, a[2]); a[3] = fmaf(P.std[3], r1 * s1, a[3]);
                     }
+                    if (P.raw) *reinterpret_cast<float4 *>(P.raw + env * 4) = make_float4(a[0], a[1], a[2], a[3]);
 #pragma unroll
                     for (int k2 = 0; k2 < 4; ++k2) a[k2] = fminf(fmaxf(a[k2], -1.0f), 1.0f);  // `nn_controller.c:171-173`
                     *reinterpret_cast<float4 *>(P.actions + env * 4) = make_float4(a[0], a[1], a[2], a[3]);
@@ -291,6 +293,29 @@ __global__ void __launch_bounds__(4 * kPolRows, 1) policy_kernel(const __grid_co
             P.epoch[1] = 0;
             P.epoch[0] = P.epoch[0] + 1;
         }
+    }
+}
+
+
+// Generalised advantage estimation over a device-resident rollout (SB3 `RolloutBuffer.compute_returns_and_advantage`,
+// the step after `collect_rollouts` in `model.learn`, `3D quad race.ipynb:820`): one thread per env walks its column
+// of the (steps, N) buffers backwards -- every access of a warp is one contiguous run.
+//   delta_t = r_t + gamma * V_{t+1} * (1 - done_t) - V_t ;  A_t = delta_t + gamma * lambda * (1 - done_t) * A_{t+1}
+// values has steps+1 rows (the last one bootstraps).  done_t ends the episode AFTER step t (the env has already been
+// reset when obs_{t+1} was written), so V_{t+1} belongs to the next episode and is masked.
+__global__ void gae_kernel(const float *rew, const float *val, const uint8_t *done, float *adv, float *ret, long long n,
+                           int steps, float gamma, float lambda) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a = 0.0f, v_next = val[(long long)steps * n + i];
+    for (int t = steps - 1; t >= 0; --t) {
+        const long long k = (long long)t * n + i;
+        const float nd = done[k] ? 0.0f : 1.0f, v = val[k];
+        const float delta = fmaf(gamma * nd, v_next, rew[k]) - v;
+        a = fmaf(gamma * lambda * nd, a, delta);
+        adv[k] = a;
+        ret[k] = a + v;
+        v_next = v;
     }
 }
 

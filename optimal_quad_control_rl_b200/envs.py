@@ -340,7 +340,8 @@ class _QuadGatesBase(_VecEnvBase):
     def rollout(self, policy, steps, deterministic=False, buffers=None):
         """collect_rollouts on the device (SB3's loop behind `model.learn`, `3D quad race.ipynb:820`): ``steps`` x
         (policy forward -> env step) enqueued back to back, no host round trip.  Returns CUDA tensors
-        ``obs (steps+1, N, D)``, ``actions (steps, N, 4)``, ``rewards (steps, N)``, ``dones (steps, N)`` (uint8);
+        ``obs (steps+1, N, D)``, ``actions (steps, N, 4)`` (clipped), ``raw_actions (steps, N, 4)`` (un-clipped samples),
+        ``rewards (steps, N)``, ``dones (steps, N)`` (uint8);
         ``obs[0]`` is the observation the rollout started from, ``obs[steps]`` the one the next rollout starts from."""
         n, d, dev = self.num_envs, self.state_len, self.device
         self._push_config()
@@ -348,11 +349,14 @@ class _QuadGatesBase(_VecEnvBase):
         if buffers is None:
             buffers = {"obs": torch.empty((steps + 1, n, d), dtype=torch.float32, device=dev),
                        "actions": torch.empty((steps, n, 4), dtype=torch.float32, device=dev),
+                       "raw_actions": torch.empty((steps, n, 4), dtype=torch.float32, device=dev),
                        "rewards": torch.empty((steps, n), dtype=torch.float32, device=dev),
                        "dones": torch.empty((steps, n), dtype=torch.uint8, device=dev)}
             buffers["obs"][0].copy_(self._obs_ring[self._ring])
         self._call("qs_rollout", policy._h, int(steps), L._vp(buffers["obs"].data_ptr()),
-                   L._vp(buffers["actions"].data_ptr()), L._vp(buffers["rewards"].data_ptr()),
+                   L._vp(buffers["actions"].data_ptr()),
+                   L._vp(buffers["raw_actions"].data_ptr()) if "raw_actions" in buffers else None,
+                   L._vp(buffers["rewards"].data_ptr()),
                    L._vp(buffers["dones"].data_ptr()), int(bool(deterministic)))
         self._obs_ring[self._ring].copy_(buffers["obs"][steps])
         return buffers

@@ -83,7 +83,7 @@ class MlpPolicy:
         except Exception:
             pass
 
-    def forward(self, obs, deterministic=False, out=None, mean_out=None):
+    def forward(self, obs, deterministic=False, out=None, mean_out=None, raw_out=None):
         """actions (N, 4) CUDA tensor <- obs (N, in_dim) float32 CUDA tensor; asynchronous on the current stream."""
         if obs.dtype != torch.float32 or not obs.is_cuda or not obs.is_contiguous() or obs.shape[1] != self.in_dim:
             raise ValueError(f"forward needs a contiguous float32 CUDA tensor of shape (N, {self.in_dim})")
@@ -92,8 +92,20 @@ class MlpPolicy:
             out = torch.empty((n, 4), dtype=torch.float32, device=obs.device)
         self._call("qs_policy_set_stream", L._vp(torch.cuda.current_stream(self.device).cuda_stream))
         self._call("qs_policy_forward", L._vp(obs.data_ptr()), n, L._vp(out.data_ptr()),
-                   L._vp(mean_out.data_ptr()) if mean_out is not None else None, int(bool(deterministic)))
+                   L._vp(mean_out.data_ptr()) if mean_out is not None else None,
+                   L._vp(raw_out.data_ptr()) if raw_out is not None else None, int(bool(deterministic)))
         return out
+
+    def set_weights(self, weights, biases, std=None):
+        """Replace the parameters (after a PPO update); shapes must not change."""
+        for l, (w, b) in enumerate(zip(weights, biases)):
+            w, b = np.ascontiguousarray(w, np.float32), np.ascontiguousarray(b, np.float32)
+            assert w.shape == self.weights[l].shape and b.shape == self.biases[l].shape
+            self.weights[l], self.biases[l] = w, b
+            self._call("qs_policy_set_layer", l, w.ctypes.data_as(L._fp), b.ctypes.data_as(L._fp))
+        if std is not None:
+            self.std[:self.out_dim] = np.asarray(std, np.float32)
+            self._call("qs_policy_set_std", self.std.ctypes.data_as(L._fp))
 
     def predict(self, observation, state=None, episode_start=None, deterministic=False):
         """SB3's ``model.predict`` signature (`3D quad race.ipynb:803`): NumPy in, ``(actions, None)`` out."""

@@ -1,0 +1,201 @@
+"""PPO over the device-resident rollout (BASELINE config 5).
+
+The reference trains with Stable-Baselines3: ``PPO("MlpPolicy", VecMonitor(env), policy_kwargs=dict(activation_fn=ReLU,
+net_arch=dict(pi=[120,120,120], vf=[120,120,120])), n_steps=1000, batch_size=5000, n_epochs=10, gamma=0.999)``
+(`3D quad race.ipynb:784-795`) and ``model.learn`` (`:820`).  SB3 is not installable here, and its rollout loop is a
+host loop with one H2D/D2H round trip per step -- exactly what the GPU env removes.  This module is the same algorithm
+with the same hyper-parameter names and defaults, split the B200 way:
+
+  collect   ``env.rollout`` -- ``n_steps`` x (tcgen05 policy forward -> fused env step) enqueued back to back, no host;
+  evaluate  values and old log-probabilities in two large batched torch forwards over the (n_steps, N, D) buffer;
+  GAE       ``qs_gae`` (one thread per env walks its column backwards);
+  update    clipped-surrogate PPO epochs in PyTorch (autograd + Adam: library GEMMs, plumbing not product);
+  publish   the new weights go back into the device policy (``MlpPolicy.set_weights``).
+
+Differences from SB3, on purpose: (1) the time-limit bootstrap ``rewards += gamma * V(terminal_observation)`` is not
+applied -- the reference's own ``infos`` alias one dict for all envs (`:589-594`), so SB3
+bootstraps every done env of a step with the value of ONE post-reset observation whenever any env timed out; a
+time-out is treated as a termination here; (2) actions are sampled by the BF16 tensor-core policy while the update
+recomputes log-probabilities in float32 (|delta mean| <= ~1e-2 against std ~1: the importance ratio starts at 1 to
+within 1e-2).  ``tests/test_gpu_ppo.py`` checks GAE against SB3's formula and that a short run improves the reward."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import time
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib as L
+from .policy import MlpPolicy
+
+
+def _mlp(in_dim, arch, out_dim, out_gain):
+    layers, d = [], in_dim
+    for h in arch:
+        lin = nn.Linear(d, h)
+        nn.init.orthogonal_(lin.weight, gain=math.sqrt(2))
+        nn.init.zeros_(lin.bias)
+        layers += [lin, nn.ReLU()]
+        d = h
+    out = nn.Linear(d, out_dim)
+    nn.init.orthogonal_(out.weight, gain=out_gain)  # SB3: 0.01 for the action net, 1 for the value net
+    nn.init.zeros_(out.bias)
+    return nn.Sequential(*layers, out)
+
+
+class PPO:
+    def __init__(self, env, net_arch=(120, 120, 120), n_steps=1000, batch_size=5000, n_epochs=10, gamma=0.999,
+                 gae_lambda=0.95, clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, learning_rate=3e-4,
+                 log_std_init=0.0, normalize_advantage=True, seed=0, tf32=True):
+        self.env, self.device = env, env.device
+        self.n_steps, self.batch_size, self.n_epochs = int(n_steps), int(batch_size), int(n_epochs)
+        self.gamma, self.gae_lambda, self.clip_range = float(gamma), float(gae_lambda), float(clip_range)
+        self.ent_coef, self.vf_coef, self.max_grad_norm = float(ent_coef), float(vf_coef), float(max_grad_norm)
+        self.normalize_advantage = normalize_advantage
+        torch.manual_seed(seed)
+        if tf32:
+            torch.backends.cuda.matmul.allow_tf32 = True
+        d = env.state_len
+        self.pi = _mlp(d, net_arch, 4, 0.01).to(self.device)
+        self.vf = _mlp(d, net_arch, 1, 1.0).to(self.device)
+        self.log_std = nn.Parameter(torch.full((4,), float(log_std_init), device=self.device))
+        self.optimizer = torch.optim.Adam([*self.pi.parameters(), *self.vf.parameters(), self.log_std], lr=learning_rate,
+                                          eps=1e-5)
+        self.actor = MlpPolicy(*self._pi_arrays(), std=self.log_std.detach().exp().cpu().numpy(), device=self.device,
+                               seed=seed)
+        self.num_timesteps = 0
+        self._lib = L.load()
+        self._started = False
+        self.buffers = None
+        self.history = []
+
+    # ------------------------------------------------------------------------------------------ plumbing
+    def _pi_arrays(self):
+        lin = [m for m in self.pi if isinstance(m, nn.Linear)]
+        return ([m.weight.detach().cpu().numpy() for m in lin], [m.bias.detach().cpu().numpy() for m in lin])
+
+    def _publish(self):
+        w, b = self._pi_arrays()
+        self.actor.set_weights(w, b, std=self.log_std.detach().exp().cpu().numpy())
+
+    def _log_prob(self, obs, raw_actions):
+        mean = self.pi(obs)
+        std = self.log_std.exp()
+        z = (raw_actions - mean) / std
+        return (-0.5 * z * z - self.log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
+
+    # ------------------------------------------------------------------------------------------ collect
+    def collect_rollouts(self):
+        env, T, n = self.env, self.n_steps, self.env.num_envs
+        if not self._started:
+            env.reset_tensor()
+            self._started = True
+        env.enable_stats(True)
+        env.stats(reset=True)
+        self._publish()
+        if self.buffers is None:
+            dev, d = self.device, env.state_len
+            self.buffers = {"obs": torch.empty((T + 1, n, d), dtype=torch.float32, device=dev),
+                            "actions": torch.empty((T, n, 4), dtype=torch.float32, device=dev),
+                            "raw_actions": torch.empty((T, n, 4), dtype=torch.float32, device=dev),
+                            "rewards": torch.empty((T, n), dtype=torch.float32, device=dev),
+                            "dones": torch.empty((T, n), dtype=torch.uint8, device=dev),
+                            "values": torch.empty((T + 1, n), dtype=torch.float32, device=dev),
+                            "log_probs": torch.empty((T, n), dtype=torch.float32, device=dev),
+                            "advantages": torch.empty((T, n), dtype=torch.float32, device=dev),
+                            "returns": torch.empty((T, n), dtype=torch.float32, device=dev)}
+        b = self.buffers
+        b["obs"][0].copy_(env._obs_ring[env._ring])
+        env.rollout(self.actor, T, buffers=b)
+        with torch.no_grad():
+            chunk = max(1, (1 << 22) // n)  # ~4M rows per forward
+            for t0 in range(0, T + 1, chunk):
+                t1 = min(T + 1, t0 + chunk)
+                b["values"][t0:t1] = self.vf(b["obs"][t0:t1].reshape(-1, env.state_len)).reshape(t1 - t0, n)
+            for t0 in range(0, T, chunk):
+                t1 = min(T, t0 + chunk)
+                b["log_probs"][t0:t1] = self._log_prob(b["obs"][t0:t1].reshape(-1, env.state_len),
+                                                       b["raw_actions"][t0:t1].reshape(-1, 4)).reshape(t1 - t0, n)
+        st = self._lib.qs_gae(L._vp(b["rewards"].data_ptr()), L._vp(b["values"].data_ptr()), L._vp(b["dones"].data_ptr()),
+                              L._vp(b["advantages"].data_ptr()), L._vp(b["returns"].data_ptr()), n, T, self.gamma,
+                              self.gae_lambda, L._vp(torch.cuda.current_stream(self.device).cuda_stream))
+        if st != 0:
+            raise L.QuadsimError(f"qs_gae failed ({st})")
+        self.num_timesteps += T * n
+        return b
+
+    # ------------------------------------------------------------------------------------------ update
+    def train(self):
+        b, T, n, d = self.buffers, self.n_steps, self.env.num_envs, self.env.state_len
+        obs = b["obs"][:T].reshape(-1, d)
+        act = b["raw_actions"].reshape(-1, 4)
+        old_lp, adv, ret = b["log_probs"].reshape(-1), b["advantages"].reshape(-1), b["returns"].reshape(-1)
+        total = T * n
+        bs = min(self.batch_size, total)
+        acc = torch.zeros(4, device=self.device)  # pg_loss, v_loss, clip_frac, approx_kl summed on the device
+        updates = 0
+        params = [*self.pi.parameters(), *self.vf.parameters(), self.log_std]
+        for _ in range(self.n_epochs):
+            perm = torch.randperm(total, device=self.device)
+            for s0 in range(0, total - bs + 1, bs):
+                idx = perm[s0:s0 + bs]
+                o, a, lp0, ad, rt = obs[idx], act[idx], old_lp[idx], adv[idx], ret[idx]
+                if self.normalize_advantage:
+                    ad = (ad - ad.mean()) / (ad.std() + 1e-8)
+                lp = self._log_prob(o, a)
+                ratio = torch.exp(lp - lp0)
+                pg = -torch.min(ad * ratio, ad * torch.clamp(ratio, 1 - self.clip_range, 1 + self.clip_range)).mean()
+                v_loss = torch.nn.functional.mse_loss(self.vf(o).squeeze(-1), rt)
+                entropy = (0.5 + 0.5 * math.log(2 * math.pi) + self.log_std).sum()
+                loss = pg + self.vf_coef * v_loss - self.ent_coef * entropy
+                self.optimizer.zero_grad(set_to_none=True)
+                loss.backward()
+                nn.utils.clip_grad_norm_(params, self.max_grad_norm)
+                self.optimizer.step()
+                with torch.no_grad():
+                    acc += torch.stack([pg, v_loss, ((ratio - 1).abs() > self.clip_range).float().mean(),
+                                        ((ratio - 1) - (lp - lp0)).mean()])
+                    updates += 1
+        a = (acc / max(1, updates)).tolist()
+        return {"pg_loss": a[0], "v_loss": a[1], "clip_frac": a[2], "approx_kl": a[3], "updates": updates}
+
+    # ------------------------------------------------------------------------------------------ learn
+    def learn(self, total_timesteps=None, iterations=None, wall_clock_s=None, log=None):
+        """``model.learn`` (`:820`): alternate collect_rollouts / train until a timestep, iteration or time budget."""
+        t_start, it = time.perf_counter(), 0
+        while True:
+            t0 = time.perf_counter()
+            b = self.collect_rollouts()
+            torch.cuda.synchronize(self.device)
+            t1 = time.perf_counter()
+            es = self.env.stats(reset=True)
+            tr = self.train()
+            torch.cuda.synchronize(self.device)
+            t2 = time.perf_counter()
+            episodes = max(1, es["dones"])
+            rec = {"iteration": it, "timesteps": self.num_timesteps, "wall_s": t2 - t_start, "collect_s": t1 - t0,
+                   "train_s": t2 - t1, "reward_per_step": es["reward_sum"] / max(1, es["env_steps"]),
+                   "ep_rew_mean": es["reward_sum"] / episodes, "ep_len_mean": es["env_steps"] / episodes,
+                   "gates_per_episode": es["gates_passed"] / episodes, "crash_rate": (es["dones"] - es["truncated"]) / episodes,
+                   "std": self.log_std.detach().exp().mean().item(), **tr}
+            self.history.append(rec)
+            if log:
+                log(rec)
+            it += 1
+            if iterations is not None and it >= iterations:
+                break
+            if total_timesteps is not None and self.num_timesteps >= total_timesteps:
+                break
+            if wall_clock_s is not None and t2 - t_start >= wall_clock_s:
+                break
+            if iterations is None and total_timesteps is None and wall_clock_s is None:
+                break
+        self._publish()
+        return self
+
+    def predict(self, observation, state=None, episode_start=None, deterministic=False):
+        self._publish()
+        return self.actor.predict(observation, deterministic=deterministic)
