@@ -14,4 +14,10 @@ def __getattr__(name):  # envs needs torch + the CUDA library: import lazily so 
     if name == "MlpPolicy":
         from . import policy
         return policy.MlpPolicy
+    if name in ("TrajectoryLog", "log_policy_run"):
+        from . import trajectory
+        return getattr(trajectory, name)
+    if name in ("export_controller", "build_controller", "CController", "track_spec"):
+        from . import codegen
+        return getattr(codegen, name)
     raise AttributeError(name)

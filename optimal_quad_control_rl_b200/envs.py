@@ -199,6 +199,16 @@ class _QuadGatesBase(_VecEnvBase):
         self._call("qs_get_state", 0, n, _f(ws), _f(d), ip(tg), ip(sc))
         return next(a for a in (ws, d, tg, sc) if a is not None)
 
+    def _get_rows(self, first, count):
+        """world_states and step_counts of envs ``first .. first+count-1`` only (what a viewer or logger needs:
+        a few hundred bytes device-to-host instead of the whole state)."""
+        if first < 0 or count < 0 or first + count > self.num_envs:
+            raise IndexError("env range out of bounds")
+        ws, sc = np.empty((count, self._ns), np.float32), np.empty(count, np.int64)
+        self._sync_stream()
+        self._call("qs_get_state", int(first), int(count), _f(ws), None, None, sc.ctypes.data_as(L._i64p))
+        return ws, sc
+
     def _set(self, ws=None, dist=None, tg=None, sc=None):
         n = self.num_envs
         ws = None if ws is None else np.ascontiguousarray(ws, np.float32).reshape(n, self._ns)
