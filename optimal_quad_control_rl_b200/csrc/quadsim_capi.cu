@@ -360,6 +360,7 @@ int qs_get_state_layout(qs_env *e, void **base, int *block_bytes, int *offsets7)
 }
 
 // ---------------------------------------------------------------------------------------------- state import / export
+static inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
 static int check_slice(qs_env *e, int64_t first, int64_t count) {
     if (first < 0 || count < 0 || first + count > e->n) return fail(e, QS_ERR_ARG, "env slice out of range");
     return QS_OK;
@@ -374,10 +375,12 @@ int qs_set_state(qs_env *e, int64_t first, int64_t count, const float *ws, const
     QS_CUDA(e, cudaSetDevice(e->device));
     const size_t b_ws = ws ? (size_t)count * e->state_len * 4 : 0, b_d = dist ? (size_t)count * 24 : 0;
     const size_t b_tg = tg ? (size_t)count * 8 : 0, b_sc = sc ? (size_t)count * 8 : 0;
-    if (int r = ensure_scratch(e, b_ws + b_d + b_tg + b_sc + 64)) return r;
+    // staging sub-buffers start on 16-byte boundaries (13 floats x an odd count would misalign the int64 arrays)
+    const size_t o_d = align16(b_ws), o_tg = o_d + align16(b_d), o_sc = o_tg + align16(b_tg);
+    if (int r = ensure_scratch(e, o_sc + b_sc + 64)) return r;
     char *base = (char *)e->scratch;
-    float *d_ws = (float *)base; float *d_d = (float *)(base + b_ws);
-    long long *d_tg = (long long *)(base + b_ws + b_d), *d_sc = (long long *)(base + b_ws + b_d + b_tg);
+    float *d_ws = (float *)base; float *d_d = (float *)(base + o_d);
+    long long *d_tg = (long long *)(base + o_tg), *d_sc = (long long *)(base + o_sc);
     if (ws) QS_CUDA(e, cudaMemcpyAsync(d_ws, ws, b_ws, cudaMemcpyHostToDevice, e->stream));
     if (dist) QS_CUDA(e, cudaMemcpyAsync(d_d, dist, b_d, cudaMemcpyHostToDevice, e->stream));
     if (tg) QS_CUDA(e, cudaMemcpyAsync(d_tg, tg, b_tg, cudaMemcpyHostToDevice, e->stream));
@@ -404,10 +407,12 @@ int qs_get_state(qs_env *e, int64_t first, int64_t count, float *ws, float *dist
     QS_CUDA(e, cudaSetDevice(e->device));
     const size_t b_ws = ws ? (size_t)count * e->state_len * 4 : 0, b_d = dist ? (size_t)count * 24 : 0;
     const size_t b_tg = tg ? (size_t)count * 8 : 0, b_sc = sc ? (size_t)count * 8 : 0;
-    if (int r = ensure_scratch(e, b_ws + b_d + b_tg + b_sc + 64)) return r;
+    // staging sub-buffers start on 16-byte boundaries (13 floats x an odd count would misalign the int64 arrays)
+    const size_t o_d = align16(b_ws), o_tg = o_d + align16(b_d), o_sc = o_tg + align16(b_tg);
+    if (int r = ensure_scratch(e, o_sc + b_sc + 64)) return r;
     char *base = (char *)e->scratch;
-    float *d_ws = (float *)base; float *d_d = (float *)(base + b_ws);
-    long long *d_tg = (long long *)(base + b_ws + b_d), *d_sc = (long long *)(base + b_ws + b_d + b_tg);
+    float *d_ws = (float *)base; float *d_d = (float *)(base + o_d);
+    long long *d_tg = (long long *)(base + o_tg), *d_sc = (long long *)(base + o_sc);
     const unsigned grid = (unsigned)((count + 255) / 256);
     if (e->variant == QS_E2E)
         qs::export_kernel<qs::kE2E><<<grid, 256, 0, e->stream>>>(e->planes, first, count, ws ? d_ws : nullptr,

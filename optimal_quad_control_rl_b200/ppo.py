@@ -55,13 +55,15 @@ def _mlp(in_dim, arch, out_dim, out_gain):
 class PPO:
     def __init__(self, env, net_arch=(120, 120, 120), n_steps=1000, batch_size=5000, n_epochs=10, gamma=0.999,
                  gae_lambda=0.95, clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, learning_rate=3e-4,
-                 log_std_init=0.0, normalize_advantage=True, seed=0, tf32=True, obs_limit=2.0e3, value_limit=1.0e3):
+                 log_std_init=0.0, normalize_advantage=True, seed=0, tf32=True, amp=False, obs_limit=2.0e3,
+                 value_limit=1.0e3):
         self.env, self.device = env, env.device
         self.n_steps, self.batch_size, self.n_epochs = int(n_steps), int(batch_size), int(n_epochs)
         self.gamma, self.gae_lambda, self.clip_range = float(gamma), float(gae_lambda), float(clip_range)
         self.ent_coef, self.vf_coef, self.max_grad_norm = float(ent_coef), float(vf_coef), float(max_grad_norm)
         self.normalize_advantage = normalize_advantage
         self.obs_limit, self.value_limit = float(obs_limit), float(value_limit)
+        self.amp = bool(amp)  # BF16 autocast of the update's GEMMs (float32 master weights, float32 losses)
         torch.manual_seed(seed)
         if tf32:
             torch.backends.cuda.matmul.allow_tf32 = True
@@ -101,7 +103,7 @@ class PPO:
                                                                                                    self._ACT_LIMIT)
 
     def _log_prob(self, obs, raw_actions, sane=False):
-        mean = self.pi(obs if sane else self._sane(obs))
+        mean = self.pi(obs if sane else self._sane(obs)).float()
         if not sane:
             raw_actions = self._sane_act(raw_actions)
         std = self.log_std.exp()
@@ -183,11 +185,13 @@ class PPO:
                     m = (ad * w).sum() / wsum
                     sd = (((ad - m) ** 2 * w).sum() / (wsum - 1).clamp_min(1.0)).sqrt()
                     ad = (ad - m) / (sd + 1e-8)
-                lp = self._log_prob(o, a, sane=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
+                    lp = self._log_prob(o, a, sane=True)
+                    v_pred = self.vf(o).squeeze(-1).float()
                 log_ratio = torch.nan_to_num(lp - lp0, nan=0.0).clamp(-20.0, 20.0)
                 ratio = torch.exp(log_ratio)
                 pg = -(torch.min(ad * ratio, ad * torch.clamp(ratio, 1 - self.clip_range, 1 + self.clip_range)) * w).sum() / wsum
-                v_loss = ((self.vf(o).squeeze(-1) - rt) ** 2 * w).sum() / wsum
+                v_loss = ((v_pred - rt) ** 2 * w).sum() / wsum
                 entropy = (0.5 + 0.5 * math.log(2 * math.pi) + self.log_std).sum()
                 loss = pg + self.vf_coef * v_loss - self.ent_coef * entropy
                 self.optimizer.zero_grad(set_to_none=True)

@@ -51,6 +51,42 @@ def test_state_roundtrip_is_exact(variant, tracks):
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("first,count", [(5, 1), (31, 3), (0, 7), (100, 33)])
+def test_state_subrange_get_set_all_fields_at_once(variant, first, count, tracks):
+    """qs_get_state / qs_set_state on an odd slice with every field requested in ONE call (13 floats x an odd count
+    once misaligned the int64 staging arrays)."""
+    import ctypes as C
+    from optimal_quad_control_rl_b200 import _lib as L
+    g = golden(f"{variant}_single_step")
+    n = 160
+    env = make_env(variant, n, tracks)
+    force(env, g["in_ws"][:n], g["in_tg"][:n], g["in_sc"][:n], g["in_dist"][:n] if variant == "e2e" else None)
+    ns = g["in_ws"].shape[1]
+    ws, tg, sc = np.empty((count, ns), np.float32), np.empty(count, np.int64), np.empty(count, np.int64)
+    dist = np.empty((count, 6), np.float32) if variant == "e2e" else None
+    fp = lambda a: a.ctypes.data_as(L._fp) if a is not None else None
+    ip = lambda a: a.ctypes.data_as(L._i64p)
+    env._call("qs_get_state", first, count, fp(ws), fp(dist), ip(tg), ip(sc))
+    sl = slice(first, first + count)
+    np.testing.assert_array_equal(ws, g["in_ws"][sl])
+    np.testing.assert_array_equal(tg, g["in_tg"][sl] % env.num_gates)
+    np.testing.assert_array_equal(sc, g["in_sc"][sl])
+    if dist is not None:
+        np.testing.assert_array_equal(dist, g["in_dist"][sl])
+    ws2, sc2 = env._get_rows(first, count)
+    np.testing.assert_array_equal(ws2, ws); np.testing.assert_array_equal(sc2, sc)
+    # write the slice back shifted by one env and read the whole state: only that slice changed
+    before = env.world_states
+    env._call("qs_set_state", first, count, fp(np.ascontiguousarray(ws[::-1])), fp(dist), ip(tg), ip(sc))
+    after = env.world_states
+    np.testing.assert_array_equal(after[sl], ws[::-1])
+    mask = np.ones(n, bool); mask[sl] = False
+    np.testing.assert_array_equal(after[mask], before[mask])
+    with pytest.raises(IndexError):
+        env._get_rows(n - 1, 2)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
 def test_gate_tables_match_reference(variant, tracks):
     k = golden("kat")
     env = make_env(variant, 4, tracks)

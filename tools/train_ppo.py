@@ -19,6 +19,8 @@ def main():
     ap.add_argument("--seconds", type=float, default=120.0)
     ap.add_argument("--iterations", type=int, default=None)
     ap.add_argument("--lr", type=float, default=3e-4)
+    ap.add_argument("--amp", action="store_true", help="BF16 autocast of the update's GEMMs")
+    ap.add_argument("--save", default=None, help="checkpoint path written at the end (model.save)")
     a = ap.parse_args()
     import optimal_quad_control_rl_b200 as Q
     if a.variant == "e2e":
@@ -28,9 +30,11 @@ def main():
     else:
         gp, gy, sp = Q.rectangle_track()
         env = Q.Quadcopter3DGatesINDI(a.num_envs, gp, gy, sp, gates_ahead=1, reset_rng="device", seed=0)
-    ppo = Q.PPO(env, n_steps=a.n_steps, batch_size=a.batch_size, n_epochs=a.n_epochs, learning_rate=a.lr)
+    ppo = Q.PPO(env, n_steps=a.n_steps, batch_size=a.batch_size, n_epochs=a.n_epochs, learning_rate=a.lr, amp=a.amp)
     ppo.learn(wall_clock_s=None if a.iterations else a.seconds, iterations=a.iterations,
               log=lambda r: print(json.dumps(r), flush=True))
+    if a.save:
+        ppo.save(a.save)
 
 
 if __name__ == "__main__":
