@@ -42,9 +42,11 @@ def parse():
     ap.add_argument("--gather-obs", nargs="?", const="nccl", default=None, choices=["nccl", "p2p"],
                     help="add the all-gather of observations per step: nccl = step kernel writes the send slot, NCCL "
                          "gathers in place; p2p = the step kernel stores its tiles into every peer's buffer itself")
-    ap.add_argument("--workload", default="step", choices=["step", "policy", "rollout"],
+    ap.add_argument("--workload", default="step", choices=["step", "policy", "rollout", "rollout_fused", "rollout_unfused"],
                     help="step: the env step alone on resident actions (the headline, default); policy: the on-device "
                          "controller forward alone (tcgen05); rollout: policy forward + env step per step, no host")
+    ap.add_argument("--rollout-steps", type=int, default=32,
+                    help="rollout_fused / rollout_unfused: env steps per qs_rollout[_fused] call (SB3 n_steps)")
     ap.add_argument("--no-stats", action="store_true", help="do not accumulate the device-side reward/flag totals")
     ap.add_argument("--graph", type=int, default=20,
                     help="replay the timed steps as a CUDA graph of this many steps (0 = one launch call per step)")
@@ -238,6 +240,24 @@ def run_ours(a):
         torch.cuda.synchronize()
 
     W, K = max(a.warmup, 3), a.steps
+    roll = a.workload in ("rollout_fused", "rollout_unfused")
+    if roll:  # collect_rollouts into (T, N, .) buffers: one fused launch per T steps, or 2T launches
+        T = max(1, min(a.rollout_steps, K))
+        K -= K % T
+        W = max(T, W - W % T)
+        a.graph = 0
+        bufs = {"obs": torch.empty((T + 1, n, env.state_len), dtype=torch.float32, device=dev),
+                "actions": torch.empty((T, n, 4), dtype=torch.float32, device=dev),
+                "raw_actions": torch.empty((T, n, 4), dtype=torch.float32, device=dev),
+                "rewards": torch.empty((T, n), dtype=torch.float32, device=dev),
+                "dones": torch.empty((T, n), dtype=torch.uint8, device=dev)}
+        bufs["obs"][0].copy_(env._obs_ring[env._ring])
+        fused = a.workload == "rollout_fused"
+
+        def one_step(i):  # noqa: F811 - called once per T env steps below
+            if i % T == 0:
+                env.rollout(pol, T, buffers=bufs, fused=fused)
+                bufs["obs"][0].copy_(bufs["obs"][T])
     for i in range(W):
         one_step(i)
     graph = None
@@ -282,6 +302,8 @@ def run_ours(a):
         launches = K
     elif a.workload == "rollout":
         launches = 2 * K
+    elif roll:
+        launches = K // T if fused else 2 * K
     st = env.stats(reset=True)
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -299,13 +321,15 @@ def run_ours(a):
             except Exception:
                 pass
             tf_peak = float(peaks.get("bf16_tflops_sustained", 1407.0))
-            out = {"metric": METRIC if a.workload == "rollout" else "policy forwards/sec", "value": value,
-                   "unit": UNIT if a.workload == "rollout" else "obs/s", "n_gpus": world, "steps": K, "warmup": W,
+            out = {"metric": METRIC if a.workload != "policy" else "policy forwards/sec", "value": value,
+                   "unit": UNIT if a.workload != "policy" else "obs/s", "n_gpus": world, "steps": K, "warmup": W,
                    "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                    "dtype": "bf16 operands / f32 accumulate (policy), f32 (env)", "data": "synthetic",
                    "config": {"workload": a.workload + "_" + workload_name(a), "policy": "24-120-120-120-4 ReLU "
                               "(c_code/neural_network.c weights), Gaussian noise + clip", "envs_per_gpu": n,
-                              "launch": "cuda-graph x%d" % a.graph if graph is not None else "per-step"},
+                              "launch": "cuda-graph x%d" % a.graph if graph is not None else
+                              ("one fused launch per %d steps" % T if roll and fused else "per-step"),
+                              **({"rollout_steps": T, "hbm_bytes_per_env_step_written": 4 * env.state_len + 37} if roll else {})},
                    "clocks": clocks, "gpu_launches": int(launches), "e2e": None}
             if a.workload == "policy":
                 ach = n * flops / (ms / K * 1e-3) / 1e12

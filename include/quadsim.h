@@ -202,6 +202,15 @@ uint64_t qs_policy_launch_count(const qs_policy *policy);
  * rew_buf (steps, N) f32, done_buf (steps, N) u8 -- all device pointers.  Asynchronous on the env's stream. */
 int qs_rollout(qs_env *env, qs_policy *policy, int steps, float *obs_buf, float *act_buf, float *raw_buf, float *rew_buf,
                uint8_t *done_buf, int deterministic);
+/* The same rollout as ONE launch of the fused closed-loop kernel: each 128-env tile stays in registers for all
+ * `steps`, the controller runs on the tensor cores in between, only the rollout buffers are written to HBM (the
+ * simulator state is read and written once per launch instead of once per step).  Same arguments and -- because reset
+ * draws and exploration noise are keyed by (seed, env, launch epoch + t) -- the same results, bit for bit, as
+ * qs_rollout.  qs_rollout_fused_supported() != 0 when the env / policy shapes fit the kernel (observation tile +
+ * layer-1 operand <= 32 KB per tile group, 4 actions, same device). */
+int qs_rollout_fused_supported(const qs_env *env, const qs_policy *policy);
+int qs_rollout_fused(qs_env *env, qs_policy *policy, int steps, float *obs_buf, float *act_buf, float *raw_buf,
+                     float *rew_buf, uint8_t *done_buf, int deterministic);
 /* SB3 `RolloutBuffer.compute_returns_and_advantage` on the device: rew/adv/ret (steps, n) f32, val (steps+1, n) f32
  * (last row = bootstrap values), done (steps, n) u8.  A_t = delta_t + gamma*lambda*(1-done_t)*A_{t+1}. */
 int qs_gae(const float *rew_dev, const float *val_dev, const uint8_t *done_dev, float *adv_dev, float *ret_dev, int64_t n,

@@ -71,6 +71,8 @@ SIGNATURES = {
     "qs_policy_forward": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int]),
     "qs_policy_launch_count": (C.c_uint64, [_vp]),
     "qs_rollout": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int]),
+    "qs_rollout_fused_supported": (C.c_int, [_vp, _vp]),
+    "qs_rollout_fused": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "qs_gae": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_float, C.c_float, _vp]),
 }
 

@@ -3,6 +3,7 @@
 // No torch, no Python: plain pointers and sizes only.
 #include "quadsim_kernels.cuh"
 #include "quadsim_policy.cuh"
+#include "quadsim_rollout.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -49,6 +50,8 @@ struct qs_env {
     cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr;
     int host_chunks = 4;   // measured on B200 + PCIe Gen5: 1 -> 4.67e8, 4 -> 5.13e8 env-steps/s at N = 2^20
     int stages = 2, step_grid = 0;  // pipeline depth and persistent grid of the step kernel
+    int l2_hints = 0;               // QS_L2_HINTS: state evict_last / streams evict_first in the step kernel
+    double l2_keep_mb = 56.0;       // QS_L2_KEEP_MB: how much of the state to pin (one die's share of the 126 MB L2)
     bool pdl = true;                // programmatic dependent launch of consecutive steps
     size_t step_smem = 0;
     std::string err;
@@ -128,6 +131,8 @@ static void refresh_params(qs_env *e) {
     P.n_gates = e->n_gates;
     P.gates_ahead = e->gates_ahead;
     P.obs_len = e->obs_len;
+    P.l2_hints = e->l2_hints;
+    P.keep_blocks = (long long)(e->l2_keep_mb * 1048576.0 / (double)e->block_bytes);
     P.max_steps = e->max_steps < 0 ? 0u : (e->max_steps > 0xFFFFFF ? 0xFFFFFFFFu : (uint32_t)e->max_steps);
     P.dt = e->dt;
     static const int rows[4] = {0, 1, 2, 5};
@@ -215,6 +220,11 @@ int qs_create(qs_env **out, int variant, int64_t num_envs, int n_gates, const fl
     // persistent step kernel: pipeline depth, shared memory, grid = SMs x resident CTAs
     if (const char *sv = getenv("QS_STAGES")) e->stages = atoi(sv) == 3 ? 3 : (atoi(sv) == 4 ? 4 : 2);
     if (const char *pv = getenv("QS_PDL")) e->pdl = atoi(pv) != 0;
+    // measured on B200 (profiles/r1/l2_pinning.md): INDI N = 2^20 41.9 -> 32.8 us/step (its 59 MB of state fits one
+    // die's share of the L2); the E2E step is issue-bound, pinning any part of its 96 MB changes nothing (-1 %)
+    e->l2_hints = variant == QS_INDI ? 1 : 0;
+    if (const char *hv = getenv("QS_L2_HINTS")) e->l2_hints = atoi(hv) != 0;
+    if (const char *kv = getenv("QS_L2_KEEP_MB")) { double v = atof(kv); if (v >= 0.0 && v <= 4096.0) e->l2_keep_mb = v; }
     const void *step_fn = step_function(e);
     e->step_smem = qs::step_smem_bytes(variant, e->stages, e->obs_len, n_gates);
     if ((c = cudaFuncSetAttribute(step_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem)) != cudaSuccess)
@@ -751,8 +761,8 @@ int qs_policy_set_std(qs_policy *p, const float *std4) {
     return QS_OK;
 }
 
-static int policy_launch(qs_policy *p, const float *obs_dev, int64_t n, float *actions_dev, float *mean_dev, float *raw_dev,
-                         int deterministic, cudaStream_t stream) {
+// uploads the weights if they changed and fills the launch-invariant part of the kernel parameters
+static int policy_params(qs_policy *p, int64_t n, int deterministic, cudaStream_t stream, qs::PolicyParams &P) {
     for (int l = 0; l <= p->n_hidden; ++l)
         if (!p->have[l]) return pfail(p, QS_ERR_STATE, "qs_policy_forward: a layer's weights are not set (qs_policy_set_layer)");
     if (cudaSetDevice(p->device) != cudaSuccess) return pfail(p, QS_ERR_CUDA, "cudaSetDevice failed");
@@ -763,13 +773,20 @@ static int policy_launch(qs_policy *p, const float *obs_dev, int64_t n, float *a
             return pfail(p, QS_ERR_CUDA, "qs_policy_forward: weight upload failed");
         p->dirty = false;
     }
-    qs::PolicyParams P{};
-    P.obs = obs_dev; P.actions = actions_dev; P.mean = mean_dev; P.raw = raw_dev; P.weights = p->w_dev; P.epoch = p->epoch_dev;
+    P.weights = p->w_dev; P.epoch = p->epoch_dev;
     P.n = n; P.env_offset = p->env_offset; P.seed = p->seed; P.in_dim = p->in_dim; P.k1 = p->k1; P.n_hidden = p->n_hidden;
     P.out_dim = p->out_dim; P.deterministic = deterministic;
     P.weight_bytes = qs::policy_weight_bytes(p->k1, p->n_hidden);
     P.tmem_cols = p->groups <= 1 ? 128u : (p->groups == 2 ? 256u : 512u);
     for (int k = 0; k < 4; ++k) P.std[k] = p->std[k];
+    return QS_OK;
+}
+
+static int policy_launch(qs_policy *p, const float *obs_dev, int64_t n, float *actions_dev, float *mean_dev, float *raw_dev,
+                         int deterministic, cudaStream_t stream) {
+    qs::PolicyParams P{};
+    if (int r = policy_params(p, n, deterministic, stream, P)) return r;
+    P.obs = obs_dev; P.actions = actions_dev; P.mean = mean_dev; P.raw = raw_dev;
     const long long tiles = (n + qs::kPolRows - 1) / qs::kPolRows;
     void *args[] = {&P};
     cudaLaunchConfig_t cfg{};
@@ -819,6 +836,55 @@ int qs_rollout(qs_env *e, qs_policy *p, int steps, float *obs_buf, float *act_bu
         if (int r = qs_step(e, act_t, obs_t + n * e->obs_len, rew_buf + (size_t)t * n, done_buf + (size_t)t * n, nullptr,
                             QS_MODE_NORMAL, QS_RESET_DEVICE)) return r;
     }
+    return QS_OK;
+}
+
+// The same rollout as ONE launch of the fused closed-loop kernel (quadsim_rollout.cuh): every tile group keeps its 128
+// quads in registers for all `steps`, the controller runs on the tensor cores in between, and only the rollout
+// buffers are written to HBM.  Same arguments, same results (bit for bit) as qs_rollout.
+int qs_rollout_fused_supported(const qs_env *e, const qs_policy *p) {
+    if (!e || !p) return 0;
+    if (p->in_dim != e->obs_len || p->out_dim != 4 || p->device != e->device) return 0;
+    if (!qs::rollout_fused_fits(p->k1, e->obs_len)) return 0;
+    int smem_max = 0;
+    if (cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device) != cudaSuccess) return 0;
+    return qs::rollout_smem_bytes(p->k1, p->n_hidden, p->groups, e->n_gates) + 1024 <= (size_t)smem_max ? 1 : 0;
+}
+
+int qs_rollout_fused(qs_env *e, qs_policy *p, int steps, float *obs_buf, float *act_buf, float *raw_buf, float *rew_buf,
+                     uint8_t *done_buf, int deterministic) {
+    QS_CHECK_ENV(e);
+    if (!p) return fail(e, QS_ERR_ARG, "qs_rollout_fused: policy is NULL");
+    if (steps < 1 || !obs_buf || !act_buf || !rew_buf || !done_buf) return fail(e, QS_ERR_ARG, "qs_rollout_fused: bad argument");
+    if (((uintptr_t)act_buf & 15) || ((uintptr_t)raw_buf & 15)) return fail(e, QS_ERR_ARG, "qs_rollout_fused: action buffers must be 16-byte aligned");
+    if (!qs_rollout_fused_supported(e, p))
+        return fail(e, QS_ERR_ARG, "qs_rollout_fused: this env / policy shape does not fit the fused kernel (use qs_rollout)");
+    if (int r = prep_launch(e, "qs_rollout_fused")) return r;
+    qs::RolloutParams R{};
+    if (int r = policy_params(p, e->n, deterministic, e->stream, R.Q)) { e->err = p->err; return r; }
+    R.S = e->P;
+    R.S.mode = QS_MODE_NORMAL; R.S.reset_source = QS_RESET_DEVICE;
+    R.obs_buf = obs_buf; R.act_buf = act_buf; R.raw_buf = raw_buf; R.rew_buf = rew_buf; R.done_buf = done_buf;
+    R.steps = steps;
+    const void *fn = e->variant == QS_E2E ? (const void *)qs::rollout_kernel<qs::kE2E> : (const void *)qs::rollout_kernel<qs::kINDI>;
+    const size_t smem = qs::rollout_smem_bytes(p->k1, p->n_hidden, p->groups, e->n_gates);
+    QS_CUDA(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long tiles = (e->n + qs::kPolRows - 1) / qs::kPolRows;
+    const long long ctas = (tiles + p->groups - 1) / p->groups;
+    void *args[] = {&R};
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(ctas < p->grid ? ctas : p->grid));
+    cfg.blockDim = dim3((unsigned)(qs::kPolRows * p->groups));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = e->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (e->pdl && p->pdl) ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    QS_CUDA(e, cudaLaunchKernelExC(&cfg, fn, args));
+    e->launches++;
+    p->launches++;
     return QS_OK;
 }
 

@@ -85,6 +85,8 @@ struct StepParams {
     unsigned long long *epoch;
     int n_gates, gates_ahead, obs_len;
     int mode, reset_source;
+    int l2_hints;  // 1: state evict_last, streams evict_first (see l2_policy_*); 0: no cache hints
+    long long keep_blocks;  // with l2_hints: only the first keep_blocks 32-env state blocks are pinned (what fits in L2)
     uint32_t max_steps;
     float dt;
     float obs_scale[4], obs_off[4];  // disturbance observation: d*scale+off  (`:414-448`)
@@ -195,8 +197,12 @@ __device__ __forceinline__ void store_dist(const Planes &s, long long i, const E
 // per-env has to be stored or read, and the stream does not depend on how N is sharded.
 template <int V> struct ResetDraws { enum : int { N = (V == kE2E ? 6 : 4) }; };
 
-__device__ __forceinline__ uint4 reset_draw(const StepParams &P, unsigned long long g, uint32_t c) {
-    const unsigned long long epoch = *reinterpret_cast<const volatile unsigned long long *>(P.epoch);
+__device__ __forceinline__ unsigned long long load_epoch(const unsigned long long *epoch) {
+    return *reinterpret_cast<const volatile unsigned long long *>(epoch);
+}
+// `epoch` = the launch counter the draw is keyed by: load_epoch(P.epoch) for a one-step launch; the fused rollout
+// kernel, which advances many steps per launch, passes (epoch at launch + step) so that both paths draw the same values
+__device__ __forceinline__ uint4 reset_draw(const StepParams &P, unsigned long long g, uint32_t c, unsigned long long epoch) {
     return philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)epoch, ((uint32_t)(epoch >> 32) << 3) | c),
                          make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
 }
@@ -234,11 +240,11 @@ __device__ __forceinline__ void fill_reset(const StepParams &P, const uint4 (&r)
 
 // every lane draws for itself (used by reset(), and by the step when many lanes of a warp terminate at once)
 template <int V>
-__device__ __forceinline__ void draw_reset(const StepParams &P, long long env, EnvState<V> &e) {
+__device__ __forceinline__ void draw_reset(const StepParams &P, long long env, EnvState<V> &e, unsigned long long epoch) {
     const unsigned long long g = (unsigned long long)(env + P.env_offset);
     uint4 r[6];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) r[c] = c < ResetDraws<V>::N ? reset_draw(P, g, c) : make_uint4(0, 0, 0, 0);
+    for (int c = 0; c < 6; ++c) r[c] = c < ResetDraws<V>::N ? reset_draw(P, g, c, epoch) : make_uint4(0, 0, 0, 0);
     fill_reset<V>(P, r, e);
 }
 
@@ -249,7 +255,7 @@ __device__ __forceinline__ void draw_reset(const StepParams &P, long long env, E
 // `need` marks the lanes that reset.  Same values as draw_reset.
 template <int V>
 __device__ __forceinline__ void draw_reset_warp(const StepParams &P, long long warp_env0, bool need, uint4 *scratch,
-                                                EnvState<V> &e) {
+                                                EnvState<V> &e, unsigned long long epoch) {
     constexpr int ND = ResetDraws<V>::N;
     const unsigned full = 0xffffffffu;
     const unsigned m = __ballot_sync(full, need);
@@ -257,7 +263,7 @@ __device__ __forceinline__ void draw_reset_warp(const StepParams &P, long long w
     const unsigned lane = threadIdx.x & 31;
     const int cnt = __popc(m);
     if (cnt * ND > 32) {  // mass termination (e.g. synchronous time-outs): per-lane is cheaper
-        if (need) draw_reset<V>(P, warp_env0 + lane, e);
+        if (need) draw_reset<V>(P, warp_env0 + lane, e, epoch);
         return;
     }
     const int which = lane / ND, c = lane - which * ND;
@@ -266,7 +272,7 @@ __device__ __forceinline__ void draw_reset_warp(const StepParams &P, long long w
     for (int k = 0; k < 32 / ND - 1; ++k) mm = (k < which) ? (mm & (mm - 1)) : mm;
     if (which < cnt) {
         const int src = __ffs(mm) - 1;
-        scratch[lane] = reset_draw(P, (unsigned long long)(warp_env0 + src + P.env_offset), c);
+        scratch[lane] = reset_draw(P, (unsigned long long)(warp_env0 + src + P.env_offset), c, epoch);
     }
     __syncwarp();
     if (need) {
@@ -389,7 +395,7 @@ __device__ __forceinline__ void residual_mlp(const StepParams &P, const float (&
     }
     float lo, hi;
     unpack2(at, lo, hi);
-    thrust = lo + hi;
+    thrust = add_rn(lo, hi);
     f32x2 a0 = pack2(P.b2[1], 0.0f), a1 = pack2(P.b2[2], 0.0f), a2 = pack2(P.b2[3], 0.0f);
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
@@ -410,9 +416,9 @@ __device__ __forceinline__ void residual_mlp(const StepParams &P, const float (&
         a2 = fma2(r01, pack2(P.wm2[64 + j], P.wm2[64 + j + 1]), a2);
         a2 = fma2(r23, pack2(P.wm2[64 + j + 2], P.wm2[64 + j + 3]), a2);
     }
-    unpack2(a0, lo, hi); mom[0] = lo + hi;
-    unpack2(a1, lo, hi); mom[1] = lo + hi;
-    unpack2(a2, lo, hi); mom[2] = lo + hi;
+    unpack2(a0, lo, hi); mom[0] = add_rn(lo, hi);
+    unpack2(a1, lo, hi); mom[1] = add_rn(lo, hi);
+    unpack2(a2, lo, hi); mom[2] = add_rn(lo, hi);
 }
 
 // sin and cos together: 3-term Cody-Waite reduction by pi/2 and degree-7/8 minimax polynomials (Cephes
@@ -427,15 +433,15 @@ __device__ __noinline__ float2 sincos_slow(float x) {
 
 __device__ __forceinline__ void sincos_fast(float x, float &sn, float &cs) {
     if (fabsf(x) > 1.0e5f) { const float2 r = sincos_slow(x); sn = r.x; cs = r.y; return; }   // also NaN/Inf
-    const float j = rintf(x * 0.636619772367581343f);
+    const float j = rintf(mul_rn(x, 0.636619772367581343f));
     const int q = (int)j;
     float a = fmaf(j, -1.5707962512969970703f, x);
     a = fmaf(j, -7.5497894158615963534e-08f, a);
     a = fmaf(j, -5.3903029534742383927e-15f, a);
-    const float z = a * a;
+    const float z = mul_rn(a, a);
     float ps = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
     ps = fmaf(ps, z, -1.6666654611e-1f);
-    const float s = fmaf(a * z, ps, a);
+    const float s = fmaf(mul_rn(a, z), ps, a);
     float pc = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
     pc = fmaf(pc, z, 4.166664568298827e-2f);
     pc = fmaf(pc, z, -0.5f);
@@ -447,6 +453,10 @@ __device__ __forceinline__ void sincos_fast(float x, float &sn, float &cs) {
 }
 
 // new = state + dt * f(state, action[, residual + disturbance])  (`:503-512`; INDI `:304`)
+// Every operation is spelled out (fmaf / __fmul_rn / __fadd_rn / __fsub_rn): nothing is left for the compiler to
+// contract one way in one kernel and another way in the next, so step_kernel and the fused rollout_kernel, which both
+// inline this function, produce the same bits.  The FMA placement is the one the compiler chose when free to (one
+// multiply-add per product term), measured <= 2e-6 scaled error against the reference's unfused float32 evaluation.
 template <int V>
 __device__ __forceinline__ void euler_step(const StepParams &P, const EnvState<V> &e, const float4 u, EnvState<V> &n) {
     const float dt = P.dt;
@@ -455,12 +465,16 @@ __device__ __forceinline__ void euler_step(const StepParams &P, const EnvState<V
     sincos_fast(e.th, sth, cth);
     sincos_fast(e.psi, sps, cps);
     // R = Rz*Ry*Rx
-    const float r00 = cps * cth, r10 = sps * cth, r20 = -sth;
-    const float r01 = sph * sth * cps - sps * cph, r11 = sph * sps * sth + cph * cps, r21 = sph * cth;
-    const float r02 = sph * sps + sth * cph * cps, r12 = -sph * cps + sps * sth * cph, r22 = cph * cth;
-    const float vbx = e.vx * r00 + e.vy * r10 + e.vz * r20;
-    const float vby = e.vx * r01 + e.vy * r11 + e.vz * r21;
-    const float vbz = e.vx * r02 + e.vy * r12 + e.vz * r22;
+    const float r00 = mul_rn(cps, cth), r10 = mul_rn(sps, cth), r20 = -sth;
+    const float r01 = fmaf(mul_rn(sph, sth), cps, -mul_rn(sps, cph));   // sph*sth*cps - sps*cph
+    const float r11 = fmaf(mul_rn(sph, sps), sth, mul_rn(cph, cps));    // sph*sps*sth + cph*cps
+    const float r21 = mul_rn(sph, cth);
+    const float r02 = fmaf(mul_rn(sth, cph), cps, mul_rn(sph, sps));    // sph*sps + sth*cph*cps
+    const float r12 = fmaf(mul_rn(sps, sth), cph, -mul_rn(sph, cps));   // -sph*cps + sps*sth*cph
+    const float r22 = mul_rn(cph, cth);
+    const float vbx = fmaf(e.vz, r20, fmaf(e.vy, r10, mul_rn(e.vx, r00)));
+    const float vby = fmaf(e.vz, r21, fmaf(e.vy, r11, mul_rn(e.vx, r01)));
+    const float vbz = fmaf(e.vz, r22, fmaf(e.vy, r12, mul_rn(e.vx, r02)));
 
     float Dx, Dy, T, dp, dq, dr;
     if (V == kE2E) {
@@ -468,52 +482,61 @@ __device__ __forceinline__ void euler_step(const StepParams &P, const EnvState<V
         const float x[10] = {w1, w2, w3, w4, vbx, vby, vbz, e.p, e.q, e.r};
         float thr, mom[3];
 #ifdef QS_EXP_NOMLP  // experiment only (tools/exp_variants.sh): what the step costs without the residual MLPs
-        thr = x[4] * P.b2[0]; mom[0] = x[5] * P.b2[1]; mom[1] = x[6] * P.b2[2]; mom[2] = x[7] * P.b2[3];
+        thr = mul_rn(x[4], P.b2[0]); mom[0] = mul_rn(x[5], P.b2[1]); mom[1] = mul_rn(x[6], P.b2[2]); mom[2] = mul_rn(x[7], P.b2[3]);
 #else
         residual_mlp(P, x, thr, mom);
 #endif
-        const float Mx = mom[0] + e.dist[0], My = mom[1] + e.dist[1], Mz = mom[2] + e.dist[2];
-        const float Fz = thr + e.dist[5];
+        const float Mx = add_rn(mom[0], e.dist[0]), My = add_rn(mom[1], e.dist[1]), Mz = add_rn(mom[2], e.dist[2]);
+        const float Fz = add_rn(thr, e.dist[5]);
         const float W1 = fmaf(4000.f, w1, 7000.f), W2 = fmaf(4000.f, w2, 7000.f);
         const float W3 = fmaf(4000.f, w3, 7000.f), W4 = fmaf(4000.f, w4, 7000.f);
-        const float sumW = (W1 + W2) + (W3 + W4);
-        const float q1 = W1 * W1, q2 = W2 * W2, q3 = W3 * W3, q4 = W4 * W4;
-        T = Fz - 4.36301076e-8f * ((q1 + q2) + (q3 + q4)) - 0.0625501332f * (vbx * vbx + vby * vby) -
-            2.7862899e-5f * vbz * sumW;
-        Dx = e.dist[3] - 1.07933887e-5f * vbx * sumW;
-        Dy = e.dist[4] - 9.65250793e-6f * vby * sumW;
-        dp = 1103.7527593819f * Mx - 0.896247240618101f * e.q * e.r - 8.79803364238411f * vby +
-             1.55842505518764e-6f * ((q1 - q2) + (q4 - q3));
-        dq = 805.152979066023f * My + 0.924315619967794f * e.p * e.r + 10.4077084541063f * vbx +
-             9.79081191626409e-7f * ((q1 - q3) + (q2 - q4));
-        dr = 486.854917234664f * Mz - 0.163583252190847f * e.p * e.q - 0.395780237098345f * e.r +
-             13.3373373580007f * ((u.y - u.x) + (u.w - u.z)) + 8.33177659850698f * ((w1 - w2) + (w3 - w4));
-        n.w[0] = fmaf(dt, 16.6666666666667f * (u.x - w1), w1);
-        n.w[1] = fmaf(dt, 16.6666666666667f * (u.y - w2), w2);
-        n.w[2] = fmaf(dt, 16.6666666666667f * (u.z - w3), w3);
-        n.w[V == kE2E ? 3 : 0] = fmaf(dt, 16.6666666666667f * (u.w - w4), w4);
+        const float sumW = add_rn(add_rn(W1, W2), add_rn(W3, W4));
+        const float q1 = mul_rn(W1, W1), q2 = mul_rn(W2, W2), q3 = mul_rn(W3, W3), q4 = mul_rn(W4, W4);
+        // T = Fz - k_w*sum(W^2) - k_h*(vbx^2 + vby^2) - k_z*vbz*sum(W)
+        T = fmaf(-4.36301076e-8f, add_rn(add_rn(q1, q2), add_rn(q3, q4)), Fz);
+        T = fmaf(-0.0625501332f, fmaf(vbx, vbx, mul_rn(vby, vby)), T);
+        T = fmaf(-mul_rn(2.7862899e-5f, vbz), sumW, T);
+        Dx = fmaf(-mul_rn(1.07933887e-5f, vbx), sumW, e.dist[3]);
+        Dy = fmaf(-mul_rn(9.65250793e-6f, vby), sumW, e.dist[4]);
+        dp = mul_rn(1103.7527593819f, Mx);
+        dp = fmaf(-mul_rn(0.896247240618101f, e.q), e.r, dp);
+        dp = fmaf(-8.79803364238411f, vby, dp);
+        dp = fmaf(1.55842505518764e-6f, add_rn(sub_rn(q1, q2), sub_rn(q4, q3)), dp);
+        dq = mul_rn(805.152979066023f, My);
+        dq = fmaf(mul_rn(0.924315619967794f, e.p), e.r, dq);
+        dq = fmaf(10.4077084541063f, vbx, dq);
+        dq = fmaf(9.79081191626409e-7f, add_rn(sub_rn(q1, q3), sub_rn(q2, q4)), dq);
+        dr = mul_rn(486.854917234664f, Mz);
+        dr = fmaf(-mul_rn(0.163583252190847f, e.p), e.q, dr);
+        dr = fmaf(-0.395780237098345f, e.r, dr);
+        dr = fmaf(13.3373373580007f, add_rn(sub_rn(u.y, u.x), sub_rn(u.w, u.z)), dr);
+        dr = fmaf(8.33177659850698f, add_rn(sub_rn(w1, w2), sub_rn(w3, w4)), dr);
+        n.w[0] = fmaf(dt, mul_rn(16.6666666666667f, sub_rn(u.x, w1)), w1);
+        n.w[1] = fmaf(dt, mul_rn(16.6666666666667f, sub_rn(u.y, w2)), w2);
+        n.w[2] = fmaf(dt, mul_rn(16.6666666666667f, sub_rn(u.z, w3)), w3);
+        n.w[V == kE2E ? 3 : 0] = fmaf(dt, mul_rn(16.6666666666667f, sub_rn(u.w, w4)), w4);
 #pragma unroll
         for (int k = 0; k < 6; ++k) n.dist[k] = e.dist[k];
     } else {
         const float Tn = e.w[0];
         T = fmaf(-8.0f, Tn, -8.0f);
-        Dx = -0.33915248f * vbx;
-        Dy = -0.4314916f * vby;
-        dp = fmaf(-33.3333333333333f, e.p, 100.0f * u.x);
-        dq = fmaf(-33.3333333333333f, e.q, 100.0f * u.y);
-        dr = fmaf(-33.3333333333333f, e.r, 66.6666666666667f * u.z);
-        n.w[0] = fmaf(dt, 33.3333333333333f * (u.w - Tn), Tn);
+        Dx = mul_rn(-0.33915248f, vbx);
+        Dy = mul_rn(-0.4314916f, vby);
+        dp = fmaf(-33.3333333333333f, e.p, mul_rn(100.0f, u.x));
+        dq = fmaf(-33.3333333333333f, e.q, mul_rn(100.0f, u.y));
+        dr = fmaf(-33.3333333333333f, e.r, mul_rn(66.6666666666667f, u.z));
+        n.w[0] = fmaf(dt, mul_rn(33.3333333333333f, sub_rn(u.w, Tn)), Tn);
     }
-    const float dvx = r00 * Dx + r01 * Dy + r02 * T;
-    const float dvy = r10 * Dx + r11 * Dy + r12 * T;
-    const float dvz = r20 * Dx + r21 * Dy + r22 * T + 9.81f;
+    const float dvx = fmaf(r02, T, fmaf(r01, Dy, mul_rn(r00, Dx)));
+    const float dvy = fmaf(r12, T, fmaf(r11, Dy, mul_rn(r10, Dx)));
+    const float dvz = add_rn(fmaf(r22, T, fmaf(r21, Dy, mul_rn(r20, Dx))), 9.81f);
     // Euler-angle kinematics (`:140-142`); tan = sin/cos with one IEEE reciprocal
     const float rc = __frcp_rn(cth);
-    const float tth = sth * rc;
-    const float qs_rc = e.q * sph + e.r * cph;
+    const float tth = mul_rn(sth, rc);
+    const float qs_rc = fmaf(e.r, cph, mul_rn(e.q, sph));
     const float dphi = fmaf(qs_rc, tth, e.p);
-    const float dth = e.q * cph - e.r * sph;
-    const float dpsi = qs_rc * rc;
+    const float dth = fmaf(-e.r, sph, mul_rn(e.q, cph));
+    const float dpsi = mul_rn(qs_rc, rc);
 
     // positions: exactly the reference's two rounded float32 operations, so every threshold test agrees bit for bit
     n.x = add_rn(e.x, mul_rn(dt, e.vx));
@@ -559,8 +582,83 @@ __device__ __forceinline__ void bulk_store(void *dst, const void *src_smem, uint
                  : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// ---- L2 residency control (126 MB L2 on B200).  The simulator state is re-read and re-written every step while
+// observations / rewards / flags stream out and actions stream in: with the state's lines marked evict_last and the
+// streams evict_first the state stays resident in L2 across consecutive step launches and stops costing HBM traffic.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_load_hint(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void bulk_store_hint(void *dst, const void *src_smem, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes), "l"(pol) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void st_hint(float4 *p, float4 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+                 ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint(float2 *p, float2 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint(float *p, float v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint(uint32_t *p, uint32_t v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint(uint8_t *p, uint8_t v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.u8 [%0], %1, %2;" ::"l"(p), "r"((uint32_t)v), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// step_counts += 1, reward, gate logic and termination flags of one env (`3D quad race.ipynb:514-566`): `e` is the
+// state before the Euler update, `n` after it.  Advances `tg` on a gate pass; shared by the step kernel and the fused
+// rollout kernel so that both produce the same bits.
+template <int V>
+__device__ __forceinline__ void reward_and_flags(const StepParams &P, const float *s_track, const EnvState<V> &e,
+                                                 const EnvState<V> &n, uint32_t &tg, uint32_t &sc, float &reward, bool &dn,
+                                                 uint32_t &fl) {
+    sc = sc < kStepMask ? sc + 1 : sc;  // step_counts += 1 (`:514`), saturating in 24 bits
+    const float4 ga = *reinterpret_cast<const float4 *>(s_track + tg * kTrackRow);
+    const float2 gcs = *reinterpret_cast<const float2 *>(s_track + tg * kTrackRow + 4);
+    const float ox = sub_rn(e.x, ga.x), oy = sub_rn(e.y, ga.y), oz = sub_rn(e.z, ga.z);
+    const float nx = sub_rn(n.x, ga.x), ny = sub_rn(n.y, ga.y), nz = sub_rn(n.z, ga.z);
+    const float d_old = norm3_rn(ox, oy, oz), d_new = norm3_rn(nx, ny, nz);
+    reward = sub_rn(d_old, d_new);
+    const float proj_old = add_rn(mul_rn(ox, gcs.x), mul_rn(oy, gcs.y));
+    const float proj_new = add_rn(mul_rn(nx, gcs.x), mul_rn(ny, gcs.y));
+    const bool plane = (proj_old < 0.0f) && (proj_new > 0.0f);
+    const float ax = fabsf(nx), ay = fabsf(ny), az = fabsf(nz);
+    const bool passed = plane && (ax < 0.5f) && (ay < 0.5f) && (az < 0.5f);
+    const bool collided = plane && ((ax > 0.5f) || (ay > 0.5f) || (az > 0.5f));
+    const bool ground = n.z > 0.0f;
+    const bool oob = (fabsf(n.x) > 10.0f) || (fabsf(n.y) > 10.0f) || (fabsf(n.p) > 1000.0f) ||
+                     (fabsf(n.q) > 1000.0f) || (fabsf(n.r) > 1000.0f);
+    const bool trunc = sc >= P.max_steps;
+    if (passed) reward = sub_rn(10.0f, mul_rn(10.0f, d_new));
+    if (collided | ground | oob) reward = -10.0f;
+    if (passed) tg = (tg + 1 == (uint32_t)P.n_gates) ? 0u : tg + 1;  // (`:556-557`)
+    dn = trunc | ground | collided | oob;
+    fl = (dn ? F_DONE : 0u) | (trunc ? F_TRUNC : 0u) | (passed ? F_PASSED : 0u) | (collided ? F_COLLISION : 0u) |
+         (ground ? F_GROUND : 0u) | (oob ? F_OOB : 0u);
+}
 
 // ------------------------------------------------------------------------------------------------ the step kernel
 // Input stage of ONE WARP: the warp's state block exactly as it lies in HBM (one bulk copy) followed by its 32
@@ -578,13 +676,20 @@ __host__ __device__ constexpr size_t step_smem_bytes(int variant, int stages, in
 
 // lane 0 of a warp: fill one of the warp's stages with the 32 envs starting at `first`
 template <int V>
-__device__ __forceinline__ void issue_warp_tile(const StepParams &P, unsigned char *st, uint64_t *bar, long long first) {
+__device__ __forceinline__ void issue_warp_tile(const StepParams &P, unsigned char *st, uint64_t *bar, long long first,
+                                                uint64_t pol_state, uint64_t pol_stream) {
     using S = Stage<V>;
     const long long rem = P.n - first;
     const uint32_t act_bytes = rem >= 32 ? 512u : (rem > 0 ? (uint32_t)rem * 16u : 0u);  // caller's buffer is not padded
     mbar_expect_tx(bar, (uint32_t)Blk<V>::BYTES + act_bytes);
-    bulk_load(st, P.s.base + (first >> 5) * (long long)Blk<V>::BYTES, Blk<V>::BYTES, bar);
-    if (act_bytes) bulk_load(st + S::ACT, P.actions + first, act_bytes, bar);
+    if (P.l2_hints) {
+        bulk_load_hint(st, P.s.base + (first >> 5) * (long long)Blk<V>::BYTES, Blk<V>::BYTES, bar,
+                       (first >> 5) < P.keep_blocks ? pol_state : pol_stream);
+        if (act_bytes) bulk_load_hint(st + S::ACT, P.actions + first, act_bytes, bar, pol_stream);
+    } else {
+        bulk_load(st, P.s.base + (first >> 5) * (long long)Blk<V>::BYTES, Blk<V>::BYTES, bar);
+        if (act_bytes) bulk_load(st + S::ACT, P.actions + first, act_bytes, bar);
+    }
 }
 
 // Persistent CTAs (grid = SMs x resident CTAs) of four INDEPENDENT warps.  Each warp owns 32 envs of the CTA's
@@ -614,6 +719,8 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < P.n_gates * kTrackRow; i += kStepThreads) s_track[i] = P.track[i];
+    const bool hints = P.l2_hints != 0;
+    const uint64_t pol_keep = hints ? l2_policy_evict_last() : 0ull, pol_stream = hints ? l2_policy_evict_first() : 0ull;
     __syncthreads();  // barrier init and track table visible to everyone
     // Everything above touched only launch constants.  From here on we read and write simulator state that the
     // previous step's grid may still be producing (programmatic dependent launch).
@@ -623,7 +730,7 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
 #pragma unroll
         for (int s = 0; s < kStages; ++s) {
             const long long t = tile0 + (long long)s * gridDim.x;
-            if (t < n_tiles) issue_warp_tile<V>(P, stages + s * S::BYTES, &full[s], t * kBlock + warp * 32);
+            if (t < n_tiles) issue_warp_tile<V>(P, stages + s * S::BYTES, &full[s], t * kBlock + warp * 32, pol_keep, pol_stream);
         }
     }
 
@@ -667,7 +774,7 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
         __syncwarp();  // the warp's inputs are in registers: refill the stage with the tile kStages ahead
         if (lane == 0) {
             const long long nt = tile + (long long)kStages * gridDim.x;
-            if (nt < n_tiles) issue_warp_tile<V>(P, st, &full[stage], nt * kBlock + warp * 32);
+            if (nt < n_tiles) issue_warp_tile<V>(P, st, &full[stage], nt * kBlock + warp * 32, pol_keep, pol_stream);
         }
 
 #ifdef QS_EXP_NOCOMPUTE  // experiment only: the memory pipeline alone (same loads and stores, no arithmetic)
@@ -675,31 +782,8 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
         float reward = u.y; const bool dn = false; const uint32_t fl = 0;
 #else
         euler_step<V>(P, e, u, n);
-        sc = sc < kStepMask ? sc + 1 : sc;  // step_counts += 1 (`:514`), saturating in 24 bits
-
-        // ---- reward and flags (`:516-566`)
-        const float4 ga = *reinterpret_cast<const float4 *>(s_track + tg * kTrackRow);
-        const float2 gcs = *reinterpret_cast<const float2 *>(s_track + tg * kTrackRow + 4);
-        const float ox = sub_rn(e.x, ga.x), oy = sub_rn(e.y, ga.y), oz = sub_rn(e.z, ga.z);
-        const float nx = sub_rn(n.x, ga.x), ny = sub_rn(n.y, ga.y), nz = sub_rn(n.z, ga.z);
-        const float d_old = norm3_rn(ox, oy, oz), d_new = norm3_rn(nx, ny, nz);
-        float reward = sub_rn(d_old, d_new);
-        const float proj_old = add_rn(mul_rn(ox, gcs.x), mul_rn(oy, gcs.y));
-        const float proj_new = add_rn(mul_rn(nx, gcs.x), mul_rn(ny, gcs.y));
-        const bool plane = (proj_old < 0.0f) && (proj_new > 0.0f);
-        const float ax = fabsf(nx), ay = fabsf(ny), az = fabsf(nz);
-        const bool passed = plane && (ax < 0.5f) && (ay < 0.5f) && (az < 0.5f);
-        const bool collided = plane && ((ax > 0.5f) || (ay > 0.5f) || (az > 0.5f));
-        const bool ground = n.z > 0.0f;
-        const bool oob = (fabsf(n.x) > 10.0f) || (fabsf(n.y) > 10.0f) || (fabsf(n.p) > 1000.0f) ||
-                         (fabsf(n.q) > 1000.0f) || (fabsf(n.r) > 1000.0f);
-        const bool trunc = sc >= P.max_steps;
-        if (passed) reward = sub_rn(10.0f, mul_rn(10.0f, d_new));
-        if (collided | ground | oob) reward = -10.0f;
-        if (passed) tg = (tg + 1 == (uint32_t)P.n_gates) ? 0u : tg + 1;  // (`:556-557`)
-        const bool dn = trunc | ground | collided | oob;
-        const uint32_t fl = (dn ? F_DONE : 0u) | (trunc ? F_TRUNC : 0u) | (passed ? F_PASSED : 0u) |
-                            (collided ? F_COLLISION : 0u) | (ground ? F_GROUND : 0u) | (oob ? F_OOB : 0u);
+        float reward; bool dn; uint32_t fl;
+        reward_and_flags<V>(P, s_track, e, n, tg, sc, reward, dn, fl);
 #endif
 
         // ---- branch logic (`:568-585`)
@@ -712,7 +796,8 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
                     if (lane == 0 && obs_in_flight) bulk_store_wait_read();
                     obs_in_flight = false;
                     __syncwarp();
-                    draw_reset_warp<V>(P, base + warp * 32, need, reinterpret_cast<uint4 *>(s_obs + warp * 32 * P.obs_len), n);
+                    draw_reset_warp<V>(P, base + warp * 32, need, reinterpret_cast<uint4 *>(s_obs + warp * 32 * P.obs_len), n,
+                                       load_epoch(P.epoch));
                 }
                 if (need) {
                     tg = 0; sc = 0;
@@ -725,22 +810,44 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
             write_world = false;
         }
         unsigned char *const gblk = P.s.base + (tile * kWarps + warp) * (long long)Blk<V>::BYTES;  // this warp's block
-        if (active) {
-            reinterpret_cast<uint32_t *>(gblk + S::META)[lane] = (tg << 24) | sc;
-            P.rew[env] = reward;
-            P.done[env] = (P.mode == kModePause) ? (uint8_t)0 : (uint8_t)(dn ? 1 : 0);
-            if (P.flags) P.flags[env] = (uint8_t)fl;
-        }
-        if (write_world) {
-            reinterpret_cast<float4 *>(gblk + S::P0)[lane] = make_float4(n.x, n.y, n.z, n.vx);
-            reinterpret_cast<float4 *>(gblk + S::P1)[lane] = make_float4(n.vy, n.vz, n.phi, n.th);
-            reinterpret_cast<float4 *>(gblk + S::P2)[lane] = make_float4(n.psi, n.p, n.q, n.r);
-            if (V == kE2E) reinterpret_cast<float4 *>(gblk + S::P3)[lane] = make_float4(n.w[0], n.w[1], n.w[2], n.w[V == kE2E ? 3 : 0]);
-            else reinterpret_cast<float *>(gblk + S::P3)[lane] = n.w[0];
-        }
-        if (V == kE2E && write_dist) {
-            reinterpret_cast<float4 *>(gblk + S::DA)[lane] = make_float4(n.dist[0], n.dist[1], n.dist[2], n.dist[5]);
-            reinterpret_cast<float2 *>(gblk + S::DB)[lane] = make_float2(n.dist[3], n.dist[4]);
+        const uint8_t dn8 = (P.mode == kModePause) ? (uint8_t)0 : (uint8_t)(dn ? 1 : 0);
+        if (!hints) {
+            if (active) {
+                reinterpret_cast<uint32_t *>(gblk + S::META)[lane] = (tg << 24) | sc;
+                P.rew[env] = reward;
+                P.done[env] = dn8;
+                if (P.flags) P.flags[env] = (uint8_t)fl;
+            }
+            if (write_world) {
+                reinterpret_cast<float4 *>(gblk + S::P0)[lane] = make_float4(n.x, n.y, n.z, n.vx);
+                reinterpret_cast<float4 *>(gblk + S::P1)[lane] = make_float4(n.vy, n.vz, n.phi, n.th);
+                reinterpret_cast<float4 *>(gblk + S::P2)[lane] = make_float4(n.psi, n.p, n.q, n.r);
+                if (V == kE2E) reinterpret_cast<float4 *>(gblk + S::P3)[lane] = make_float4(n.w[0], n.w[1], n.w[2], n.w[V == kE2E ? 3 : 0]);
+                else reinterpret_cast<float *>(gblk + S::P3)[lane] = n.w[0];
+            }
+            if (V == kE2E && write_dist) {
+                reinterpret_cast<float4 *>(gblk + S::DA)[lane] = make_float4(n.dist[0], n.dist[1], n.dist[2], n.dist[5]);
+                reinterpret_cast<float2 *>(gblk + S::DB)[lane] = make_float2(n.dist[3], n.dist[4]);
+            }
+        } else {  // the same stores with L2 priorities: state lines stay, result streams leave first
+            const uint64_t pol_state = (tile * kWarps + warp) < P.keep_blocks ? pol_keep : pol_stream;
+            if (active) {
+                st_hint(reinterpret_cast<uint32_t *>(gblk + S::META) + lane, (tg << 24) | sc, pol_state);
+                st_hint(P.rew + env, reward, pol_stream);
+                st_hint(P.done + env, dn8, pol_stream);
+                if (P.flags) st_hint(P.flags + env, (uint8_t)fl, pol_stream);
+            }
+            if (write_world) {
+                st_hint(reinterpret_cast<float4 *>(gblk + S::P0) + lane, make_float4(n.x, n.y, n.z, n.vx), pol_state);
+                st_hint(reinterpret_cast<float4 *>(gblk + S::P1) + lane, make_float4(n.vy, n.vz, n.phi, n.th), pol_state);
+                st_hint(reinterpret_cast<float4 *>(gblk + S::P2) + lane, make_float4(n.psi, n.p, n.q, n.r), pol_state);
+                if (V == kE2E) st_hint(reinterpret_cast<float4 *>(gblk + S::P3) + lane, make_float4(n.w[0], n.w[1], n.w[2], n.w[V == kE2E ? 3 : 0]), pol_state);
+                else st_hint(reinterpret_cast<float *>(gblk + S::P3) + lane, n.w[0], pol_state);
+            }
+            if (V == kE2E && write_dist) {
+                st_hint(reinterpret_cast<float4 *>(gblk + S::DA) + lane, make_float4(n.dist[0], n.dist[1], n.dist[2], n.dist[5]), pol_state);
+                st_hint(reinterpret_cast<float2 *>(gblk + S::DB) + lane, make_float2(n.dist[3], n.dist[4]), pol_state);
+            }
         }
 
         if (write_obs_tile) {
@@ -764,7 +871,8 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0 && bytes) {
-                    bulk_store(dst, warp_obs, bytes);
+                    if (hints) bulk_store_hint(dst, warp_obs, bytes, pol_stream);
+                    else bulk_store(dst, warp_obs, bytes);
                     for (int p = 0; p < P.n_peers; ++p)  // NVLink: the tile leaves for every peer while the next one is computed
                         bulk_store(P.peer_obs[p] + (P.peer_row_offset + base + warp * 32) * P.obs_len, warp_obs, bytes);
                 }
@@ -840,7 +948,7 @@ __global__ void __launch_bounds__(kBlock) observe_kernel(const __grid_constant__
         EnvState<V> e;
         uint32_t tg;
         if (reset_all) {
-            draw_reset<V>(P, env, e);
+            draw_reset<V>(P, env, e, load_epoch(P.epoch));
             tg = 0;
             field<V, Blk<V>::META, uint32_t>(P.s, env) = 0;
             store_world<V>(P.s, env, e);

@@ -347,12 +347,14 @@ class _QuadGatesBase(_VecEnvBase):
                    L._vp(self._flags_ring[k].data_ptr()), self._mode(), L.RESET_DEVICE)
         return obs_d, self._rew_ring[k], self._done_ring[k], self._flags_ring[k]
 
-    def rollout(self, policy, steps, deterministic=False, buffers=None):
+    def rollout(self, policy, steps, deterministic=False, buffers=None, fused=None):
         """collect_rollouts on the device (SB3's loop behind `model.learn`, `3D quad race.ipynb:820`): ``steps`` x
         (policy forward -> env step) enqueued back to back, no host round trip.  Returns CUDA tensors
         ``obs (steps+1, N, D)``, ``actions (steps, N, 4)`` (clipped), ``raw_actions (steps, N, 4)`` (un-clipped samples),
         ``rewards (steps, N)``, ``dones (steps, N)`` (uint8);
-        ``obs[0]`` is the observation the rollout started from, ``obs[steps]`` the one the next rollout starts from."""
+        ``obs[0]`` is the observation the rollout started from, ``obs[steps]`` the one the next rollout starts from.
+        ``fused``: True = ONE launch of the closed-loop kernel (quads stay in registers for all ``steps``; same results
+        bit for bit), False = 2*steps launches, None = fused whenever the shapes fit."""
         n, d, dev = self.num_envs, self.state_len, self.device
         self._push_config()
         self._sync_stream()
@@ -363,7 +365,9 @@ class _QuadGatesBase(_VecEnvBase):
                        "rewards": torch.empty((steps, n), dtype=torch.float32, device=dev),
                        "dones": torch.empty((steps, n), dtype=torch.uint8, device=dev)}
             buffers["obs"][0].copy_(self._obs_ring[self._ring])
-        self._call("qs_rollout", policy._h, int(steps), L._vp(buffers["obs"].data_ptr()),
+        if fused is None:
+            fused = bool(self._lib.qs_rollout_fused_supported(self._h, policy._h))
+        self._call("qs_rollout_fused" if fused else "qs_rollout", policy._h, int(steps), L._vp(buffers["obs"].data_ptr()),
                    L._vp(buffers["actions"].data_ptr()),
                    L._vp(buffers["raw_actions"].data_ptr()) if "raw_actions" in buffers else None,
                    L._vp(buffers["rewards"].data_ptr()),
