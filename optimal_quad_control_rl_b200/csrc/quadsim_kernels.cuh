@@ -373,6 +373,9 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
 // Weights are kernel parameters (constant bank, warp-uniform): LDCU.128 brings four of them into uniform
 // registers and each FFMA2 consumes a PAIR of hidden units -- 336 FFMA2 + 168 LDCU.128 for the 672 MACs,
 // measured on B200 at the same FMA/clk as scalar FFMA in half the issue slots (profiles/microbench).
+// The hidden-unit loops stay FULLY unrolled although that makes the E2E step kernel 4000 SASS instructions long:
+// rolled (8 trips, weights indexed by the trip counter) the constant-bank operands become indexed loads and the step
+// takes 227 us instead of 60.6 us at N = 2^20 (measured, profiles/r1/experiments.md).
 __device__ __forceinline__ void residual_mlp(const StepParams &P, const float (&x)[10], float &thrust, float (&mom)[3]) {
     f32x2 xx[10];
 #pragma unroll
