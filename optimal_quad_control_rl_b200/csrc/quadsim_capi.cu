@@ -774,7 +774,7 @@ static int policy_params(qs_policy *p, int64_t n, int deterministic, cudaStream_
         p->dirty = false;
     }
     P.weights = p->w_dev; P.epoch = p->epoch_dev;
-    P.n = n; P.env_offset = p->env_offset; P.seed = p->seed; P.in_dim = p->in_dim; P.k1 = p->k1; P.n_hidden = p->n_hidden;
+    P.n = n; P.env_offset = p->env_offset; P.seed = p->seed; P.in_dim = p->in_dim; P.k1 = p->k1; P.n_hidden = p->n_hidden; P.hidden = p->hidden;
     P.out_dim = p->out_dim; P.deterministic = deterministic;
     P.weight_bytes = qs::policy_weight_bytes(p->k1, p->n_hidden);
     P.tmem_cols = p->groups <= 1 ? 128u : (p->groups == 2 ? 256u : 512u);

@@ -376,48 +376,58 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
 // The hidden-unit loops stay FULLY unrolled although that makes the E2E step kernel 4000 SASS instructions long:
 // rolled (8 trips, weights indexed by the trip counter) the constant-bank operands become indexed loads and the step
 // takes 227 us instead of 60.6 us at N = 2^20 (measured, profiles/r1/experiments.md).
+#ifndef QS_MLP_CHAINS
+#define QS_MLP_CHAINS 4  // independent FFMA2 accumulator chains per trip (2 or 4); same sums, same order, same bits
+#endif
 __device__ __forceinline__ void residual_mlp(const StepParams &P, const float (&x)[10], float &thrust, float (&mom)[3]) {
+    constexpr int C = QS_MLP_CHAINS;  // hidden-unit pairs in flight: a dependent FFMA2 issues every ~4 cycles, so
+                                      // 2 chains cap a warp at IPC 0.5 inside the MLP; 4 chains double its ILP
     f32x2 xx[10];
 #pragma unroll
     for (int k = 0; k < 10; ++k) xx[k] = pack2(x[k], x[k]);
-    // four hidden units per trip: each LDCU.128 of W1^T feeds two FFMA2
     f32x2 at = pack2(P.b2[0], 0.0f);
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-        f32x2 h01 = pack2(P.bt1[j], P.bt1[j + 1]), h23 = pack2(P.bt1[j + 2], P.bt1[j + 3]);
+    for (int j = 0; j < 32; j += 2 * C) {
+        f32x2 h[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) h[c] = pack2(P.bt1[j + 2 * c], P.bt1[j + 2 * c + 1]);
 #pragma unroll
         for (int k = 0; k < 7; ++k) {
-            h01 = fma2(pack2(P.wt1[k * 32 + j], P.wt1[k * 32 + j + 1]), xx[k], h01);
-            h23 = fma2(pack2(P.wt1[k * 32 + j + 2], P.wt1[k * 32 + j + 3]), xx[k], h23);
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                h[c] = fma2(pack2(P.wt1[k * 32 + j + 2 * c], P.wt1[k * 32 + j + 2 * c + 1]), xx[k], h[c]);
         }
-        float h0, h1, h2, h3;
-        unpack2(h01, h0, h1);
-        unpack2(h23, h2, h3);
-        at = fma2(pack2(fmaxf(h0, 0.0f), fmaxf(h1, 0.0f)), pack2(P.wt2[j], P.wt2[j + 1]), at);
-        at = fma2(pack2(fmaxf(h2, 0.0f), fmaxf(h3, 0.0f)), pack2(P.wt2[j + 2], P.wt2[j + 3]), at);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {  // ascending hidden units into ONE output chain: the order fixes the bits
+            float h0, h1;
+            unpack2(h[c], h0, h1);
+            at = fma2(pack2(fmaxf(h0, 0.0f), fmaxf(h1, 0.0f)), pack2(P.wt2[j + 2 * c], P.wt2[j + 2 * c + 1]), at);
+        }
     }
     float lo, hi;
     unpack2(at, lo, hi);
     thrust = add_rn(lo, hi);
     f32x2 a0 = pack2(P.b2[1], 0.0f), a1 = pack2(P.b2[2], 0.0f), a2 = pack2(P.b2[3], 0.0f);
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-        f32x2 h01 = pack2(P.bm1[j], P.bm1[j + 1]), h23 = pack2(P.bm1[j + 2], P.bm1[j + 3]);
+    for (int j = 0; j < 32; j += 2 * C) {
+        f32x2 h[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) h[c] = pack2(P.bm1[j + 2 * c], P.bm1[j + 2 * c + 1]);
 #pragma unroll
         for (int k = 0; k < 10; ++k) {
-            h01 = fma2(pack2(P.wm1[k * 32 + j], P.wm1[k * 32 + j + 1]), xx[k], h01);
-            h23 = fma2(pack2(P.wm1[k * 32 + j + 2], P.wm1[k * 32 + j + 3]), xx[k], h23);
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                h[c] = fma2(pack2(P.wm1[k * 32 + j + 2 * c], P.wm1[k * 32 + j + 2 * c + 1]), xx[k], h[c]);
         }
-        float h0, h1, h2, h3;
-        unpack2(h01, h0, h1);
-        unpack2(h23, h2, h3);
-        const f32x2 r01 = pack2(fmaxf(h0, 0.0f), fmaxf(h1, 0.0f)), r23 = pack2(fmaxf(h2, 0.0f), fmaxf(h3, 0.0f));
-        a0 = fma2(r01, pack2(P.wm2[j], P.wm2[j + 1]), a0);
-        a0 = fma2(r23, pack2(P.wm2[j + 2], P.wm2[j + 3]), a0);
-        a1 = fma2(r01, pack2(P.wm2[32 + j], P.wm2[32 + j + 1]), a1);
-        a1 = fma2(r23, pack2(P.wm2[32 + j + 2], P.wm2[32 + j + 3]), a1);
-        a2 = fma2(r01, pack2(P.wm2[64 + j], P.wm2[64 + j + 1]), a2);
-        a2 = fma2(r23, pack2(P.wm2[64 + j + 2], P.wm2[64 + j + 3]), a2);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float h0, h1;
+            unpack2(h[c], h0, h1);
+            const f32x2 r = pack2(fmaxf(h0, 0.0f), fmaxf(h1, 0.0f));
+            a0 = fma2(r, pack2(P.wm2[j + 2 * c], P.wm2[j + 2 * c + 1]), a0);
+            a1 = fma2(r, pack2(P.wm2[32 + j + 2 * c], P.wm2[32 + j + 2 * c + 1]), a1);
+            a2 = fma2(r, pack2(P.wm2[64 + j + 2 * c], P.wm2[64 + j + 2 * c + 1]), a2);
+        }
     }
     unpack2(a0, lo, hi); mom[0] = add_rn(lo, hi);
     unpack2(a1, lo, hi); mom[1] = add_rn(lo, hi);

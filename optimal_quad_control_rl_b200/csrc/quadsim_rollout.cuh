@@ -39,7 +39,7 @@ struct RolloutParams {
 
 // the f32 staging tile of a group lives behind the layer-1 slabs of its A buffer
 __host__ __device__ constexpr bool rollout_fused_fits(int k1, int obs_len) {
-    return (k1 / 8) * kSlab + kPolRows * obs_len * 4 <= (kPolHidden / 8) * kSlab;
+    return (k1 / 8) * kSlab + kPolRows * obs_len * 4 <= (kPolHidden / 8 - 1) * kSlab;  // slab 15 holds a constant
 }
 // dynamic shared memory = the policy kernel's + the track table
 __host__ __device__ constexpr size_t rollout_smem_bytes(int k1, int n_hidden, int groups, int n_gates) {
@@ -89,6 +89,8 @@ __global__ void __launch_bounds__(4 * kPolRows, 1) rollout_kernel(const __grid_c
     mbar_wait(bar_w, 0);
 
     const uint32_t a_smem = smem_u32(s_a), w_smem = smem_u32(s_w);
+    const bool const_last = Q.hidden <= kPolHidden - 8;  // slab 15 = {0 x 7, 1}: written once, see epilogue_tail
+    if (const_last) init_const_slab(s_a + tid * 16);
     const unsigned long long step_epoch0 = load_epoch(P.epoch);
     const unsigned long long pol_epoch0 = Q.deterministic ? 0ull : load_epoch(Q.epoch);
     const size_t nD = (size_t)P.n * D;
@@ -180,20 +182,14 @@ __global__ void __launch_bounds__(4 * kPolRows, 1) rollout_kernel(const __grid_c
                 phase ^= 1u;
                 tc_fence_after();
                 if (!last) {
+                    uint32_t v0[32];
 #pragma unroll 1
-                    for (int c = 0; c < kPolHidden / 32; ++c) {
-                        uint32_t v0[32];
+                    for (int c = 0; c < 3; ++c) {
                         tmem_ld32(t_lane + (uint32_t)c * 32u, v0);
                         tmem_ld_wait();
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            uint32_t w[4];
-#pragma unroll
-                            for (int h = 0; h < 4; ++h)
-                                w[h] = pack_relu_bf16(__uint_as_float(v0[q * 8 + 2 * h]), __uint_as_float(v0[q * 8 + 2 * h + 1]));
-                            *reinterpret_cast<uint4 *>(s_a + (c * 4 + q) * kSlab + tid * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-                        }
+                        relu_pack_store<4>(v0, s_a + (c * 4) * kSlab + tid * 16);
                     }
+                    epilogue_tail(t_lane, s_a + tid * 16, const_last, v0);
                 } else {
                     uint32_t v[8];
                     tmem_ld8(t_lane, v);
