@@ -251,7 +251,7 @@ def run_ours(a):
                 "raw_actions": torch.empty((T, n, 4), dtype=torch.float32, device=dev),
                 "rewards": torch.empty((T, n), dtype=torch.float32, device=dev),
                 "dones": torch.empty((T, n), dtype=torch.uint8, device=dev)}
-        bufs["obs"][0].copy_(env._obs_ring[env._ring])
+        bufs["obs"][0].copy_(env.current_obs_tensor())
         fused = a.workload == "rollout_fused"
 
         def one_step(i):  # noqa: F811 - called once per T env steps below

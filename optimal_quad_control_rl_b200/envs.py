@@ -145,6 +145,9 @@ class _QuadGatesBase(_VecEnvBase):
         self.pause = False
         self.last_flags = np.zeros(n, dtype=np.uint8)
         self._pushed = None
+        self._host_ring = None     # pinned NumPy-facing output buffers of the host fast path (lazy)
+        self._host_ptrs = []
+        self._ring_stale = False   # the device obs ring lags the state after a host-path step
 
     # ------------------------------------------------------------------------------------------ plumbing
     def _call(self, name, *args):
@@ -180,6 +183,9 @@ class _QuadGatesBase(_VecEnvBase):
         h, self._h = getattr(self, "_h", None), None
         if h:
             self._lib.qs_destroy(h)
+        ptrs, self._host_ptrs, self._host_ring = getattr(self, "_host_ptrs", []), [], None
+        for p in ptrs:  # arrays handed out earlier must not be used after close()
+            self._lib.qs_host_free(p)
 
     def __del__(self):  # pragma: no cover
         try:
@@ -239,6 +245,7 @@ class _QuadGatesBase(_VecEnvBase):
         self._sync_stream()
         k = self._next_slot()
         self._call("qs_observe", L._vp(self._obs_ring[k].data_ptr()))
+        self._ring_stale = False
         self.states = self._obs_ring[k].cpu().numpy()
         return self.states
 
@@ -275,6 +282,7 @@ class _QuadGatesBase(_VecEnvBase):
         dones = np.asarray(dones, dtype=bool)
         k = self._next_slot()
         self._call("qs_observe", L._vp(self._obs_ring[k].data_ptr()))
+        self._ring_stale = False
         self._apply_host_reset(dones, self._obs_ring[k])
         self.states = self._obs_ring[k].cpu().numpy()
         return self.states
@@ -290,11 +298,62 @@ class _QuadGatesBase(_VecEnvBase):
     def step_async(self, actions):
         self.actions = actions
 
+    def _pinned(self, shape, dtype):
+        """A NumPy array over page-locked host memory (qs_host_alloc): device copies into it are asynchronous DMA."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = self._lib.qs_host_alloc(max(nbytes, 1))
+        if not p:
+            raise L.QuadsimError("qs_host_alloc failed")
+        self._host_ptrs.append(p)
+        return np.frombuffer((C.c_char * max(nbytes, 1)).from_address(p), dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def _step_wait_host(self, mode):
+        """NumPy-facing fast path (``reset_rng="device"``): ONE ``qs_step_host`` call -- chunk-pipelined H2D of the
+        actions, step kernel, D2H of obs / reward / done / flags -- into a ring of pinned NumPy arrays.  The returned
+        arrays are recycled after ``obs_buffers`` further steps (SB3 copies them into its rollout buffer within one)."""
+        n = self.num_envs
+        if self._host_ring is None:
+            self._host_ring = [{"obs": self._pinned((n, self.state_len), np.float32), "rew": self._pinned((n,), np.float32),
+                                "done": self._pinned((n,), np.uint8), "flags": self._pinned((n,), np.uint8)}
+                               for _ in self._obs_ring]
+            self._host_act = self._pinned((n, 4), np.float32)
+        k = self._next_slot()
+        h = self._host_ring[k]
+        np.copyto(self._host_act, np.asarray(self.actions).reshape(n, 4), casting="unsafe")
+        vp = lambda a: L._vp(a.ctypes.data)
+        self._call("qs_step_host", vp(self._host_act), vp(h["obs"]), vp(h["rew"]), vp(h["done"]), vp(h["flags"]), mode,
+                   L.RESET_DEVICE)
+        self._ring_stale = True
+        return h["obs"], h["rew"], h["done"].view(np.bool_), h["flags"]
+
+    def current_obs_tensor(self):
+        """The observations of the current state as a CUDA tensor (N, D): what ``step_tensor`` / ``rollout`` last wrote,
+        recomputed from the state if NumPy-path steps ran in between."""
+        if self._ring_stale:
+            self._push_config()
+            self._sync_stream()
+            self._call("qs_observe", L._vp(self._obs_ring[self._ring].data_ptr()))
+            self._ring_stale = False
+        return self._obs_ring[self._ring]
+
     def step_wait(self):
         """step_wait (`:501-595`), NumPy in / NumPy out.  Returns fresh arrays every call."""
         n = self.num_envs
         self._push_config()
         self._sync_stream()
+        if self.reset_rng == "device":
+            mode = self._mode()
+            obs, rewards, dones, flags = self._step_wait_host(mode)
+            if mode != L.MODE_PAUSE:
+                self.states = obs
+            self.dones, self.last_flags = dones, flags
+            info = {}
+            idx = np.flatnonzero(dones)
+            if idx.size:
+                info["terminal_observation"] = self.states[idx[-1]]
+            if (flags & L.F_TRUNCATED).any():
+                info["TimeLimit.truncated"] = True
+            return self.states, rewards, dones, [info] * n
         act = np.ascontiguousarray(self.actions, dtype=np.float32).reshape(n, 4)
         self._act_dev.copy_(torch.from_numpy(act))
         mode = self._mode()
@@ -330,6 +389,7 @@ class _QuadGatesBase(_VecEnvBase):
         self._sync_stream()
         k = self._next_slot()
         self._call("qs_reset_all", L._vp(self._obs_ring[k].data_ptr()))
+        self._ring_stale = False
         return self._obs_ring[k]
 
     def step_tensor(self, actions, obs_out=None):
@@ -345,6 +405,7 @@ class _QuadGatesBase(_VecEnvBase):
         self._call("qs_step", L._vp(actions.data_ptr()), L._vp(obs_d.data_ptr()),
                    L._vp(self._rew_ring[k].data_ptr()), L._vp(self._done_ring[k].data_ptr()),
                    L._vp(self._flags_ring[k].data_ptr()), self._mode(), L.RESET_DEVICE)
+        self._ring_stale = obs_out is not None  # the ring slot itself was not written
         return obs_d, self._rew_ring[k], self._done_ring[k], self._flags_ring[k]
 
     def rollout(self, policy, steps, deterministic=False, buffers=None, fused=None):
@@ -364,7 +425,7 @@ class _QuadGatesBase(_VecEnvBase):
                        "raw_actions": torch.empty((steps, n, 4), dtype=torch.float32, device=dev),
                        "rewards": torch.empty((steps, n), dtype=torch.float32, device=dev),
                        "dones": torch.empty((steps, n), dtype=torch.uint8, device=dev)}
-            buffers["obs"][0].copy_(self._obs_ring[self._ring])
+            buffers["obs"][0].copy_(self.current_obs_tensor())
         if fused is None:
             fused = bool(self._lib.qs_rollout_fused_supported(self._h, policy._h))
         self._call("qs_rollout_fused" if fused else "qs_rollout", policy._h, int(steps), L._vp(buffers["obs"].data_ptr()),
@@ -373,6 +434,7 @@ class _QuadGatesBase(_VecEnvBase):
                    L._vp(buffers["rewards"].data_ptr()),
                    L._vp(buffers["dones"].data_ptr()), int(bool(deterministic)))
         self._obs_ring[self._ring].copy_(buffers["obs"][steps])
+        self._ring_stale = False
         return buffers
 
     def set_obs_peers(self, peer_ptrs, row_offset):

@@ -132,7 +132,7 @@ class PPO:
                             "weights": torch.empty((T, n), dtype=torch.float32, device=dev),
                             "returns": torch.empty((T, n), dtype=torch.float32, device=dev)}
         b = self.buffers
-        b["obs"][0].copy_(env._obs_ring[env._ring])
+        b["obs"][0].copy_(env.current_obs_tensor())
         env.rollout(self.actor, T, buffers=b)
         with torch.no_grad():
             torch.nan_to_num_(b["rewards"], nan=0.0, posinf=0.0, neginf=0.0)  # one NaN would poison a whole GAE column

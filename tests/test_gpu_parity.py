@@ -421,3 +421,42 @@ def test_errors_are_reported_not_raised_across_abi(tracks):
     assert b"weights" in lib.qs_last_error(h)
     assert lib.qs_set_state(h, 10, 100, None, None, None, None) == -1
     lib.qs_destroy(h)
+
+
+@pytest.mark.parametrize("variant,n", [("e2e", 5000), ("indi", 40000)])
+def test_numpy_step_uses_pinned_host_path_and_matches_tensor_path(variant, n, tracks):
+    """reset_rng="device": env.step(NumPy) is ONE qs_step_host call into a ring of pinned arrays; it must return what
+    the zero-copy tensor path returns for the same seed, keep earlier outputs intact for obs_buffers steps, and hand a
+    consistent observation tensor to a rollout that follows."""
+    import torch
+    ranges = None
+    if variant == "e2e":
+        import optimal_quad_control_rl_b200 as Q
+        ranges = Q.training_disturbance_ranges()
+    a = make_env(variant, n, tracks, ranges=ranges, reset_rng="device", seed=5, obs_buffers=3)
+    b = make_env(variant, n, tracks, ranges=ranges, reset_rng="device", seed=5, obs_buffers=3)
+    a.max_steps = b.max_steps = 7
+    oa = a.reset()
+    ob = b.reset_tensor().cpu().numpy()
+    np.testing.assert_array_equal(oa, ob)
+    rng = np.random.default_rng(0)
+    prev = None
+    for t in range(12):
+        act = rng.uniform(-1, 1, (n, 4)).astype(np.float32)
+        l0 = a.launch_count
+        obs, rew, done, infos = a.step(act if t % 2 else act.astype(np.float64))  # float64 actions are cast
+        tobs, trew, tdone, tfl = b.step_tensor(torch.from_numpy(act).cuda())
+        np.testing.assert_array_equal(obs, tobs.cpu().numpy())
+        np.testing.assert_array_equal(rew, trew.cpu().numpy())
+        np.testing.assert_array_equal(done, tdone.cpu().numpy().astype(bool))
+        assert done.dtype == np.bool_ and obs.dtype == np.float32 and a.states is obs
+        if prev is not None:  # the previous step's arrays are still what they were (SB3 reads them after env.step)
+            np.testing.assert_array_equal(prev[0], prev[1])
+        prev = (obs, obs.copy())
+        if done.any():
+            assert "terminal_observation" in infos[0]
+        if t == 6:
+            assert done.all() and infos[0].get("TimeLimit.truncated")
+    np.testing.assert_array_equal(a.current_obs_tensor().cpu().numpy(), obs)
+    np.testing.assert_array_equal(a.world_states, b.world_states)
+    a.close(); b.close()
