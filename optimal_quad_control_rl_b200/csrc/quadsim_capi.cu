@@ -220,8 +220,8 @@ int qs_create(qs_env **out, int variant, int64_t num_envs, int n_gates, const fl
     // persistent step kernel: pipeline depth, shared memory, grid = SMs x resident CTAs
     if (const char *sv = getenv("QS_STAGES")) e->stages = atoi(sv) == 3 ? 3 : (atoi(sv) == 4 ? 4 : 2);
     if (const char *pv = getenv("QS_PDL")) e->pdl = atoi(pv) != 0;
-    // measured on B200 (profiles/r1/l2_pinning.md): INDI N = 2^20 41.9 -> 32.8 us/step (its 59 MB of state fits one
-    // die's share of the L2); the E2E step is issue-bound, pinning any part of its 96 MB changes nothing (-1 %)
+    // measured on B200 (profiles/r1/l2_pinning.md): INDI N = 2^20 41.9 -> 32.8 us/step, DRAM traffic per launch 177 ->
+    // 136 MB; for E2E (96 MB of state + 122 MB of streams per step) the hints change neither traffic nor time
     e->l2_hints = variant == QS_INDI ? 1 : 0;
     if (const char *hv = getenv("QS_L2_HINTS")) e->l2_hints = atoi(hv) != 0;
     if (const char *kv = getenv("QS_L2_KEEP_MB")) { double v = atof(kv); if (v >= 0.0 && v <= 4096.0) e->l2_keep_mb = v; }
