@@ -173,6 +173,23 @@ __device__ __forceinline__ void group_barrier(int group) {  // the 128 threads o
     asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
 }
 
+// mean + std * N(0,1) (`c_code/nn_controller.c:158-169`): Box-Muller on ONE Philox block keyed by (seed, global env,
+// launch epoch).  Shared by policy_kernel and the fused rollout_kernel (epoch = launch epoch + step) so that both
+// sample the same actions, bit for bit.
+__device__ __forceinline__ void add_exploration_noise(const PolicyParams &P, long long env, unsigned long long epoch,
+                                                      float (&a)[4]) {
+    const unsigned long long g = (unsigned long long)(env + P.env_offset);
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)epoch, ((uint32_t)(epoch >> 32) << 3) | 7u),
+                                  make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
+    const float u0 = sub_rn(1.0f, u01(r.x)), u1 = u01(r.y), u2 = sub_rn(1.0f, u01(r.z)), u3 = u01(r.w);  // u0, u2 in (0,1]
+    const float r0 = sqrtf(mul_rn(-2.0f, logf(u0))), r1 = sqrtf(mul_rn(-2.0f, logf(u2)));
+    float s0, c0, s1, c1;
+    sincospif(mul_rn(2.0f, u1), &s0, &c0);
+    sincospif(mul_rn(2.0f, u3), &s1, &c1);
+    a[0] = fmaf(P.std[0], mul_rn(r0, c0), a[0]); a[1] = fmaf(P.std[1], mul_rn(r0, s0), a[1]);
+    a[2] = fmaf(P.std[2], mul_rn(r1, c1), a[2]); a[3] = fmaf(P.std[3], mul_rn(r1, s1), a[3]);
+}
+
 // Persistent, ONE CTA per SM made of `groups` (<= 4) independent tile groups of 128 threads.  The groups share the
 // weights in shared memory; each owns an A-operand buffer (32 KB), 128 accumulator columns of TMEM, an mbarrier and
 // a named block barrier, and walks its own 128-env tiles: thread r of a group owns row r of the tile (its
@@ -300,19 +317,7 @@ __global__ void __launch_bounds__(4 * kPolRows, 1) policy_kernel(const __grid_co
                 float a[4] = {__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])};
                 if (active) {
                     if (P.mean) *reinterpret_cast<float4 *>(P.mean + env * 4) = make_float4(a[0], a[1], a[2], a[3]);
-                    if (!P.deterministic) {  // Box-Muller on one Philox block keyed by (seed, global env, launch epoch)
-                        const unsigned long long g = (unsigned long long)(env + P.env_offset);
-                        const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)epoch,
-                                                                 ((uint32_t)(epoch >> 32) << 3) | 7u),
-                                                      make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
-                        const float u0 = 1.0f - u01(r.x), u1 = u01(r.y), u2 = 1.0f - u01(r.z), u3 = u01(r.w);  // u0,u2 in (0,1]
-                        const float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
-                        float s0, c0, s1, c1;
-                        sincospif(2.0f * u1, &s0, &c0);
-                        sincospif(2.0f * u3, &s1, &c1);
-                        a[0] = fmaf(P.std[0], r0 * c0, a[0]); a[1] = fmaf(P.std[1], r0 * s0, a[1]);
-                        a[2] = fmaf(P.std[2], r1 * c1, a[2]); a[3] = fmaf(P.std[3], r1 * s1, a[3]);
-                    }
+                    if (!P.deterministic) add_exploration_noise(P, env, epoch, a);
                     if (P.raw) *reinterpret_cast<float4 *>(P.raw + env * 4) = make_float4(a[0], a[1], a[2], a[3]);
 #pragma unroll
                     for (int k2 = 0; k2 < 4; ++k2) a[k2] = fminf(fmaxf(a[k2], -1.0f), 1.0f);  // `nn_controller.c:171-173`

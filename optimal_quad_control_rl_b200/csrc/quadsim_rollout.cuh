@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(4 * kPolRows, 1) rollout_kernel(const __grid_c
     uint64_t *bar_mma_all = bar_w + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + 64);
     const int groups = blockDim.x / kPolRows;
-    const int group = threadIdx.x / kPolRows, tid = threadIdx.x % kPolRows, warp = tid >> 5, lane = tid & 31;
+    const int group = threadIdx.x / kPolRows, tid = threadIdx.x % kPolRows, warp = tid >> 5;
     constexpr int kABytes = (kPolHidden / 8) * kSlab;
     unsigned char *s_a = smem_raw + 128 + group * kABytes;
     unsigned char *s_w = smem_raw + 128 + groups * kABytes;
@@ -195,20 +195,7 @@ __global__ void __launch_bounds__(4 * kPolRows, 1) rollout_kernel(const __grid_c
                     tmem_ld8(t_lane, v);
                     tmem_ld_wait();
                     float a[4] = {__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])};
-                    if (!Q.deterministic) {  // same Philox block and Box-Muller as policy_kernel, epoch = launch epoch + t
-                        const unsigned long long g = (unsigned long long)(env + Q.env_offset);
-                        const unsigned long long ep = pol_epoch0 + (unsigned long long)t;
-                        const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)ep,
-                                                                 ((uint32_t)(ep >> 32) << 3) | 7u),
-                                                      make_uint2((uint32_t)Q.seed, (uint32_t)(Q.seed >> 32)));
-                        const float u0 = 1.0f - u01(r.x), u1 = u01(r.y), u2 = 1.0f - u01(r.z), u3 = u01(r.w);
-                        const float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
-                        float s0, c0, s1, c1;
-                        sincospif(2.0f * u1, &s0, &c0);
-                        sincospif(2.0f * u3, &s1, &c1);
-                        a[0] = fmaf(Q.std[0], r0 * c0, a[0]); a[1] = fmaf(Q.std[1], r0 * s0, a[1]);
-                        a[2] = fmaf(Q.std[2], r1 * c1, a[2]); a[3] = fmaf(Q.std[3], r1 * s1, a[3]);
-                    }
+                    if (!Q.deterministic) add_exploration_noise(Q, env, pol_epoch0 + (unsigned long long)t, a);
                     const size_t k4 = ((size_t)t * (size_t)P.n + (size_t)env) * 4;
                     if (active && R.raw_buf) *reinterpret_cast<float4 *>(R.raw_buf + k4) = make_float4(a[0], a[1], a[2], a[3]);
 #pragma unroll
