@@ -178,3 +178,34 @@ def test_generator_rejects_inconsistent_inputs(tracks):
     assert "d_min[4] = {-1.0, -1.0, -1.0, -1.0}" in src and "extern uint8_t target_gate_index;" in hdr
     src, hdr = G.network_sources(w, b, activation="tanh")
     assert "nn_tanh(y" in src and "void nn_forward(const float* input, float* output);" in hdr
+
+
+@pytest.mark.parametrize("variant", ["e2e", "indi"])
+def test_track_spec_reproduces_the_reference_gate_tables(variant, tracks):
+    """track_spec (the host-side __init__ precompute, `3D quad race.ipynb:309-319`) against the frozen reference tables
+    (K3: for the rectangle track they are the constants baked into `c_code/nn_controller.c:40-60`)."""
+    from optimal_quad_control_rl_b200 import codegen as G
+    k = golden("kat")
+    gp, gy, sp = tracks[variant]
+    spec = G.track_spec(gp, gy, sp, 1, variant)
+    np.testing.assert_array_equal(spec.gate_pos_rel, k[f"{variant}_gate_pos_rel"])
+    np.testing.assert_array_equal(spec.gate_yaw_rel, k[f"{variant}_gate_yaw_rel"])
+    assert spec.gate_pos.dtype == np.float32 and spec.num_gates == len(gy)
+
+
+def test_ppo_log_summary_finds_the_plateau(tmp_path):
+    """tools/ppo_summary.py on a synthetic log: plateau = first 5-iteration mean within 2 % of the final level."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import ppo_summary
+    rows = []
+    for i in range(100):
+        r = 100.0 * min(1.0, i / 40.0)
+        rows.append({"iteration": i, "timesteps": (i + 1) * 1000, "wall_s": 1.0 + i, "collect_s": 0.01, "train_s": 0.99,
+                     "ep_rew_mean": r, "ep_len_mean": 1200.0, "gates_per_episode": r / 10, "pg_loss": 0.0})
+    p = tmp_path / "log.jsonl"
+    p.write_text("\n".join(json.dumps(r) for r in rows))
+    s = ppo_summary.summarise(str(p))
+    assert s["iterations"] == 100 and s["final_ep_rew_mean"] == 100.0 and not s["nan"]
+    assert 40.0 <= s["plateau_wall_s"] <= 46.0 and s["train_s_per_iter"] == 0.99
