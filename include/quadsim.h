@@ -155,6 +155,21 @@ int qs_apply_reset(qs_env *env, int64_t count, const int32_t *env_index, const f
  * Buffers from qs_host_alloc are pinned and make the copies asynchronous DMA. */
 int qs_step_host(qs_env *env, const float *actions_host, float *obs_host, float *rew_host, uint8_t *done_host,
                  uint8_t *flags_host, int mode, int reset_source);
+/* The same step for the arrays a NumPy caller really has: `actions_host` is (num_envs,4) float32 or float64
+ * (`step_async` keeps whatever array it is given, `3D quad race.ipynb:498-499`) in pageable or pinned memory, converted
+ * chunk by chunk into a pinned staging buffer while the previous chunk is on the bus.  `info` (may be NULL; needs
+ * flags_host) returns what the reference's per-env `infos` loop (`:589-594`) computes: the HIGHEST done env index
+ * (whose observation row ends up as the one aliased dict's "terminal_observation"; -1 = none) and whether ANY env hit
+ * max_steps ("TimeLimit.truncated").  The caller scans nothing. */
+typedef enum { QS_F32 = 0, QS_F64 = 1 } qs_dtype;
+typedef struct {
+    int64_t last_done_index; /* -1 when no env is done (always -1 in QS_MODE_PAUSE, whose dones are cleared `:570-572`) */
+    int64_t n_done;
+    int32_t any_truncated;
+    int32_t reserved;
+} qs_step_info;
+int qs_step_host_ex(qs_env *env, const void *actions_host, int actions_dtype, float *obs_host, float *rew_host,
+                    uint8_t *done_host, uint8_t *flags_host, int mode, int reset_source, qs_step_info *info);
 int qs_reset_all_host(qs_env *env, float *obs_host);
 int qs_observe_host(qs_env *env, float *obs_host);
 void *qs_host_alloc(size_t bytes);
@@ -199,9 +214,11 @@ uint64_t qs_policy_launch_count(const qs_policy *policy);
  *   act_buf[t] = policy(obs_buf[t]);  obs_buf[t+1], rew_buf[t], done_buf[t] = step(act_buf[t])   (fused device reset)
  * obs_buf (steps+1, N, obs_len) f32 with obs_buf[0] = current observations, act_buf (steps, N, 4) f32 (clipped, what
  * the env received), raw_buf (steps, N, 4) f32 or NULL (un-clipped samples, what SB3 keeps in its RolloutBuffer),
- * rew_buf (steps, N) f32, done_buf (steps, N) u8 -- all device pointers.  Asynchronous on the env's stream. */
+ * rew_buf (steps, N) f32, done_buf (steps, N) u8, flags_buf (steps, N) u8 or NULL (the QS_F_* bits of every step:
+ * QS_F_TRUNCATED is what the reference reports as infos["TimeLimit.truncated"], `3D quad race.ipynb:592-593`, which SB3's
+ * time-limit bootstrap needs) -- all device pointers.  Asynchronous on the env's stream. */
 int qs_rollout(qs_env *env, qs_policy *policy, int steps, float *obs_buf, float *act_buf, float *raw_buf, float *rew_buf,
-               uint8_t *done_buf, int deterministic);
+               uint8_t *done_buf, uint8_t *flags_buf, int deterministic);
 /* The same rollout as ONE launch of the fused closed-loop kernel: each 128-env tile stays in registers for all
  * `steps`, the controller runs on the tensor cores in between, only the rollout buffers are written to HBM (the
  * simulator state is read and written once per launch instead of once per step).  Same arguments and -- because reset
@@ -210,7 +227,7 @@ int qs_rollout(qs_env *env, qs_policy *policy, int steps, float *obs_buf, float 
  * layer-1 operand <= 32 KB per tile group, 4 actions, same device). */
 int qs_rollout_fused_supported(const qs_env *env, const qs_policy *policy);
 int qs_rollout_fused(qs_env *env, qs_policy *policy, int steps, float *obs_buf, float *act_buf, float *raw_buf,
-                     float *rew_buf, uint8_t *done_buf, int deterministic);
+                     float *rew_buf, uint8_t *done_buf, uint8_t *flags_buf, int deterministic);
 /* SB3 `RolloutBuffer.compute_returns_and_advantage` on the device: rew/adv/ret (steps, n) f32, val (steps+1, n) f32
  * (last row = bootstrap values), done (steps, n) u8.  A_t = delta_t + gamma*lambda*(1-done_t)*A_{t+1}. */
 int qs_gae(const float *rew_dev, const float *val_dev, const uint8_t *done_dev, float *adv_dev, float *ret_dev, int64_t n,

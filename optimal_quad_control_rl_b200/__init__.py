@@ -8,9 +8,9 @@ def __getattr__(name):  # envs needs torch + the CUDA library: import lazily so 
     if name in ("Quadcopter3DGates", "Quadcopter3DGatesINDI", "load_residual_weights"):
         from . import envs
         return getattr(envs, name)
-    if name == "PPO":
+    if name in ("PPO", "VecMonitor", "ActorCriticPolicy", "a8_bootstrap_"):
         from . import ppo
-        return ppo.PPO
+        return getattr(ppo, name)
     if name == "MlpPolicy":
         from . import policy
         return policy.MlpPolicy

@@ -26,6 +26,13 @@ class QsStats(C.Structure):
                 ("ground_collisions", C.c_uint64), ("out_of_bounds", C.c_uint64)]
 
 
+class QsStepInfo(C.Structure):
+    _fields_ = [("last_done_index", C.c_int64), ("n_done", C.c_int64), ("any_truncated", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+F32, F64 = 0, 1
+
 # name -> (restype, argtypes); every symbol include/quadsim.h declares
 SIGNATURES = {
     "qs_state_len": (C.c_int, [C.c_int]),
@@ -53,6 +60,7 @@ SIGNATURES = {
     "qs_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int]),
     "qs_apply_reset": (C.c_int, [_vp, C.c_int64, _i32p, _fp, _fp, _vp]),
     "qs_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int]),
+    "qs_step_host_ex": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.POINTER(QsStepInfo)]),
     "qs_reset_all_host": (C.c_int, [_vp, _vp]),
     "qs_observe_host": (C.c_int, [_vp, _vp]),
     "qs_host_alloc": (_vp, [C.c_size_t]),
@@ -70,9 +78,9 @@ SIGNATURES = {
     "qs_policy_set_env_offset": (C.c_int, [_vp, C.c_int64]),
     "qs_policy_forward": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int]),
     "qs_policy_launch_count": (C.c_uint64, [_vp]),
-    "qs_rollout": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int]),
+    "qs_rollout": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "qs_rollout_fused_supported": (C.c_int, [_vp, _vp]),
-    "qs_rollout_fused": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int]),
+    "qs_rollout_fused": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "qs_gae": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_float, C.c_float, _vp]),
 }
 

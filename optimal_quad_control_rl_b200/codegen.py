@@ -255,7 +255,7 @@ def _policy_arrays(policy):
     """(weights, biases, std) from an ``MlpPolicy`` / ``PPO`` of this package, an SB3 model, or a tuple."""
     if isinstance(policy, (tuple, list)) and len(policy) == 3:
         return policy
-    if hasattr(policy, "actor"):  # our PPO: publish the float32 master weights first
+    if getattr(policy, "actor", None) is not None:  # our PPO with a device actor: publish the float32 master weights first
         policy._publish()
         policy = policy.actor
     if hasattr(policy, "weights") and hasattr(policy, "biases"):

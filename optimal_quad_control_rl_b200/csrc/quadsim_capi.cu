@@ -42,6 +42,7 @@ struct qs_env {
     StepParams P{};  // weights live here
     // staging for the host-buffer entry points
     float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr;
+    float *act_stage = nullptr;  // pinned host staging for pageable / float64 actions (qs_step_host_ex)
     uint8_t *h_done = nullptr, *h_flags = nullptr;
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -139,8 +140,11 @@ static void refresh_params(qs_env *e) {
     for (int k = 0; k < 4; ++k) {  // 2*(d-lo)/(hi-lo)-1 with the lo==hi widening of `:419-442`
         double lo = e->ranges[2 * rows[k]], hi = e->ranges[2 * rows[k] + 1];
         if (lo == hi) { lo -= 1; hi += 1; }
-        P.obs_scale[k] = (float)(2.0 / (hi - lo));
-        P.obs_off[k] = (float)(-2.0 * lo / (hi - lo) - 1.0);
+        // a float32 ranges array (the ctor default) is evaluated in float32 by the reference, a float64 one in float64
+        const double span = e->ranges_f64 ? hi - lo : (double)((float)hi - (float)lo);
+        P.obs_lo[k] = (float)lo;
+        P.obs_lo2[k] = e->ranges_f64 ? (float)(lo - (double)P.obs_lo[k]) : 0.0f;
+        P.obs_scale[k] = (float)(2.0 / span);
     }
     for (int k = 0; k < 3; ++k) P.rd.start[k] = e->start_pos[k];
     for (int k = 0; k < 6; ++k) {
@@ -252,6 +256,7 @@ int qs_destroy(qs_env *e) {
     Planes &s = e->planes;
     cudaFree(s.base); cudaFree(e->epoch_dev); cudaFree(e->track_dev); cudaFree(e->stats_dev); cudaFree(e->scratch);
     cudaFree(e->h_act); cudaFree(e->h_obs); cudaFree(e->h_rew); cudaFree(e->h_done); cudaFree(e->h_flags);
+    if (e->act_stage) cudaFreeHost(e->act_stage);
     if (e->copy_a) cudaStreamDestroy(e->copy_a);
     if (e->copy_b) cudaStreamDestroy(e->copy_b);
     if (e->ev_in) cudaEventDestroy(e->ev_in);
@@ -330,6 +335,10 @@ int qs_set_obs_peers(qs_env *e, int n_peers, void *const *peer_obs_bases, int64_
     for (int p = 0; p < 7; ++p) e->P.peer_obs[p] = p < n_peers ? (float *)peer_obs_bases[p] : nullptr;
     for (int p = 0; p < n_peers; ++p)
         if (!peer_obs_bases[p] || ((uintptr_t)peer_obs_bases[p] & 15)) return fail(e, QS_ERR_ARG, "qs_set_obs_peers: NULL or misaligned peer buffer");
+    // the kernel sends a tile to the peers with the same TMA bulk store as to the local buffer, whose 16-byte
+    // alignment it tests on the LOCAL destination only: the peer rows must be aligned the same way
+    if (n_peers && (row_offset < 0 || ((row_offset * e->obs_len * 4) & 15)))
+        return fail(e, QS_ERR_ARG, "qs_set_obs_peers: row_offset * obs_len * 4 must be a non-negative multiple of 16");
     e->P.n_peers = n_peers;
     e->P.peer_row_offset = row_offset;
     return QS_OK;
@@ -568,10 +577,22 @@ static int ensure_io(qs_env *e) {
 // stream A carries  H2D(actions c) -> step kernel(chunk c)  and stream B the D2H of chunk c's outputs, so the
 // upload of chunk c+1 overlaps the download of chunk c.  All chunk launches read the same RNG epoch; the last one
 // advances it, so the result is bit-identical to one qs_step over device buffers.
-int qs_step_host(qs_env *e, const float *act, float *obs, float *rew, uint8_t *done, uint8_t *flags, int mode,
-                 int reset_source) {
+// Actions may be float32 or float64 (the reference keeps whatever array the caller passed, `3D quad race.ipynb:498-499`)
+// in pageable or pinned memory: pageable / float64 input is converted chunk by chunk into an internal pinned staging
+// buffer while the previous chunk is on the bus.  `info` (optional) receives what step_wait's `infos` loop needs
+// (`:589-594`): the highest done env index and whether any env was truncated, so the caller scans nothing.
+static bool is_pinned_host(const void *p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+int qs_step_host_ex(qs_env *e, const void *act, int act_dtype, float *obs, float *rew, uint8_t *done, uint8_t *flags,
+                    int mode, int reset_source, qs_step_info *info) {
     QS_CHECK_ENV(e);
     if (int r = check_step_args(e, act, obs, rew, done, mode, reset_source, "qs_step_host")) return r;
+    if (act_dtype != QS_F32 && act_dtype != QS_F64) return fail(e, QS_ERR_ARG, "qs_step_host: actions must be float32 or float64");
+    if (info && !flags) return fail(e, QS_ERR_ARG, "qs_step_host: info needs the flags buffer");
     if (int r = ensure_io(e)) return r;
     if (int r = prep_launch(e, "qs_step_host")) return r;
     StepParams &P = e->P;
@@ -582,6 +603,8 @@ int qs_step_host(qs_env *e, const float *act, float *obs, float *rew, uint8_t *d
     long long per = (tiles + e->host_chunks - 1) / e->host_chunks;
     if (per < 256) per = tiles < 256 ? tiles : 256;  // >= 32768 envs per chunk: below that the copies are latency-bound
     const bool want_obs = obs && mode != QS_MODE_PAUSE;
+    const bool stage = act_dtype == QS_F64 || !is_pinned_host(act);
+    if (stage && !e->act_stage) QS_CUDA(e, cudaHostAlloc((void **)&e->act_stage, (size_t)e->n * 16, cudaHostAllocDefault));
     QS_CUDA(e, cudaEventRecord(e->ev_in, e->stream));
     QS_CUDA(e, cudaStreamWaitEvent(e->copy_a, e->ev_in, 0));
     QS_CUDA(e, cudaStreamWaitEvent(e->copy_b, e->ev_in, 0));
@@ -589,7 +612,18 @@ int qs_step_host(qs_env *e, const float *act, float *obs, float *rew, uint8_t *d
         const long long t1 = t0 + per < tiles ? t0 + per : tiles;
         const size_t first = (size_t)t0 * qs::kBlock;
         const size_t cnt = (size_t)((t1 * qs::kBlock < e->n ? t1 * qs::kBlock : e->n)) - first;
-        QS_CUDA(e, cudaMemcpyAsync(e->h_act + first * 4, act + first * 4, cnt * 16, cudaMemcpyHostToDevice, e->copy_a));
+        const float *src = (const float *)act + first * 4;
+        if (stage) {  // the previous step's uploads completed before that call returned: the staging buffer is free
+            float *dst = e->act_stage + first * 4;
+            if (act_dtype == QS_F64) {
+                const double *s64 = (const double *)act + first * 4;
+                for (size_t i = 0; i < cnt * 4; ++i) dst[i] = (float)s64[i];
+            } else {
+                memcpy(dst, src, cnt * 16);
+            }
+            src = dst;
+        }
+        QS_CUDA(e, cudaMemcpyAsync(e->h_act + first * 4, src, cnt * 16, cudaMemcpyHostToDevice, e->copy_a));
         if (int r = launch_step(e, t0, t1, t1 == tiles, e->copy_a, false)) return r;
         QS_CUDA(e, cudaEventRecord(e->ev_k, e->copy_a));
         QS_CUDA(e, cudaStreamWaitEvent(e->copy_b, e->ev_k, 0));
@@ -604,7 +638,24 @@ int qs_step_host(qs_env *e, const float *act, float *obs, float *rew, uint8_t *d
     QS_CUDA(e, cudaEventRecord(e->ev_out, e->copy_b));
     QS_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_out, 0));  // later work on the handle's stream is ordered after us
     QS_CUDA(e, cudaEventSynchronize(e->ev_out));
+    if (info) {  // one pass over the flag bytes that just arrived (1 B/env): nothing for the caller to scan
+        int64_t last = -1, nd = 0;
+        uint8_t any = 0;
+        const uint8_t *f = flags;
+        for (int64_t i = 0; i < e->n; ++i) {
+            any |= f[i];
+            if (f[i] & QS_F_DONE) { last = i; ++nd; }
+        }
+        info->last_done_index = (mode == QS_MODE_PAUSE) ? -1 : last;
+        info->n_done = (mode == QS_MODE_PAUSE) ? 0 : nd;
+        info->any_truncated = (any & QS_F_TRUNCATED) ? 1 : 0;
+    }
     return QS_OK;
+}
+
+int qs_step_host(qs_env *e, const float *act, float *obs, float *rew, uint8_t *done, uint8_t *flags, int mode,
+                 int reset_source) {
+    return qs_step_host_ex(e, act, QS_F32, obs, rew, done, flags, mode, reset_source, nullptr);
 }
 
 static int observe_host(qs_env *e, float *obs, int reset_all) {
@@ -821,7 +872,7 @@ int qs_policy_forward(qs_policy *p, const float *obs_dev, int64_t n, float *acti
 // launches enqueued back to back on the env's stream (PDL-chained), no host round trip.  obs[0] must hold the
 // current observations (qs_reset_all / the previous rollout's obs[steps]).
 int qs_rollout(qs_env *e, qs_policy *p, int steps, float *obs_buf, float *act_buf, float *raw_buf, float *rew_buf,
-               uint8_t *done_buf, int deterministic) {
+               uint8_t *done_buf, uint8_t *flags_buf, int deterministic) {
     QS_CHECK_ENV(e);
     if (!p) return fail(e, QS_ERR_ARG, "qs_rollout: policy is NULL");
     if (steps < 1 || !obs_buf || !act_buf || !rew_buf || !done_buf) return fail(e, QS_ERR_ARG, "qs_rollout: bad argument");
@@ -833,8 +884,8 @@ int qs_rollout(qs_env *e, qs_policy *p, int steps, float *obs_buf, float *act_bu
         float *obs_t = obs_buf + (size_t)t * n * e->obs_len, *act_t = act_buf + (size_t)t * n * 4;
         float *raw_t = raw_buf ? raw_buf + (size_t)t * n * 4 : nullptr;
         if (int r = policy_launch(p, obs_t, e->n, act_t, nullptr, raw_t, deterministic, e->stream)) { e->err = p->err; return r; }
-        if (int r = qs_step(e, act_t, obs_t + n * e->obs_len, rew_buf + (size_t)t * n, done_buf + (size_t)t * n, nullptr,
-                            QS_MODE_NORMAL, QS_RESET_DEVICE)) return r;
+        if (int r = qs_step(e, act_t, obs_t + n * e->obs_len, rew_buf + (size_t)t * n, done_buf + (size_t)t * n,
+                            flags_buf ? flags_buf + (size_t)t * n : nullptr, QS_MODE_NORMAL, QS_RESET_DEVICE)) return r;
     }
     return QS_OK;
 }
@@ -852,7 +903,7 @@ int qs_rollout_fused_supported(const qs_env *e, const qs_policy *p) {
 }
 
 int qs_rollout_fused(qs_env *e, qs_policy *p, int steps, float *obs_buf, float *act_buf, float *raw_buf, float *rew_buf,
-                     uint8_t *done_buf, int deterministic) {
+                     uint8_t *done_buf, uint8_t *flags_buf, int deterministic) {
     QS_CHECK_ENV(e);
     if (!p) return fail(e, QS_ERR_ARG, "qs_rollout_fused: policy is NULL");
     if (steps < 1 || !obs_buf || !act_buf || !rew_buf || !done_buf) return fail(e, QS_ERR_ARG, "qs_rollout_fused: bad argument");
@@ -865,6 +916,7 @@ int qs_rollout_fused(qs_env *e, qs_policy *p, int steps, float *obs_buf, float *
     R.S = e->P;
     R.S.mode = QS_MODE_NORMAL; R.S.reset_source = QS_RESET_DEVICE;
     R.obs_buf = obs_buf; R.act_buf = act_buf; R.raw_buf = raw_buf; R.rew_buf = rew_buf; R.done_buf = done_buf;
+    R.flags_buf = flags_buf;
     R.steps = steps;
     const void *fn = e->variant == QS_E2E ? (const void *)qs::rollout_kernel<qs::kE2E> : (const void *)qs::rollout_kernel<qs::kINDI>;
     const size_t smem = qs::rollout_smem_bytes(p->k1, p->n_hidden, p->groups, e->n_gates);

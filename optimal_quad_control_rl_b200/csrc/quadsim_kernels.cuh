@@ -89,7 +89,9 @@ struct StepParams {
     long long keep_blocks;  // with l2_hints: only the first keep_blocks 32-env state blocks are pinned (what fits in L2)
     uint32_t max_steps;
     float dt;
-    float obs_scale[4], obs_off[4];  // disturbance observation: d*scale+off  (`:414-448`)
+    // disturbance observation 2*(d-lo)/(hi-lo)-1 (`:414-448`) as ((d - lo_hi) - lo_lo) * scale - 1: the subtraction
+    // comes first, as in the reference, so narrow ranges far from 0 do not cancel; lo_hi + lo_lo carries a float64 lo
+    float obs_lo[4], obs_lo2[4], obs_scale[4];
     ResetDist rd;
     // residual MLPs in KERNEL layout (qs_set_residual_weights transposes): layer 1 is [in][hidden] so that two
     // adjacent hidden units form one 64-bit constant-bank operand of a packed FFMA2
@@ -311,10 +313,11 @@ __device__ __forceinline__ void write_obs(const StepParams &P, const float *s_tr
             nx = (nx + 1 == (uint32_t)ng) ? 0u : nx + 1;
             o4p[4 + i] = *reinterpret_cast<const float4 *>(s_track + nx * kTrackRow + 8);
         }
-        o4p[4 + P.gates_ahead] = make_float4(fmaf(e.dist[0], P.obs_scale[0], P.obs_off[0]),
-                                             fmaf(e.dist[1], P.obs_scale[1], P.obs_off[1]),
-                                             fmaf(e.dist[2], P.obs_scale[2], P.obs_off[2]),
-                                             fmaf(e.dist[5], P.obs_scale[3], P.obs_off[3]));
+        o4p[4 + P.gates_ahead] = make_float4(
+            fmaf(sub_rn(sub_rn(e.dist[0], P.obs_lo[0]), P.obs_lo2[0]), P.obs_scale[0], -1.0f),
+            fmaf(sub_rn(sub_rn(e.dist[1], P.obs_lo[1]), P.obs_lo2[1]), P.obs_scale[1], -1.0f),
+            fmaf(sub_rn(sub_rn(e.dist[2], P.obs_lo[2]), P.obs_lo2[2]), P.obs_scale[2], -1.0f),
+            fmaf(sub_rn(sub_rn(e.dist[5], P.obs_lo[3]), P.obs_lo2[3]), P.obs_scale[3], -1.0f));
     } else {
         o[0] = o0; o[1] = o1; o[2] = o2; o[3] = o3; o[4] = o4; o[5] = e.vz; o[6] = e.phi; o[7] = e.th;
         o[8] = yaw; o[9] = e.p; o[10] = e.q; o[11] = e.r; o[12] = e.w[0];
@@ -875,6 +878,8 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
             const int rows = rem < 32 ? (rem < 0 ? 0 : (int)rem) : 32;
             float *dst = P.obs + (base + warp * 32) * P.obs_len;
             const uint32_t bytes = (uint32_t)rows * (uint32_t)P.obs_len * 4u;
+            // (peer destinations: base pointers are 16-byte aligned and qs_set_obs_peers rejects a row offset that
+            // would misalign them, so the local test covers every destination of the tile)
             const bool bulk = ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) && ((bytes & 15u) == 0);
             if (bulk) {  // the warp's rows are contiguous in the (N,D) output: one TMA bulk store
                 fence_proxy_async();

@@ -34,6 +34,7 @@ struct RolloutParams {
     float *raw_buf;   // (steps, n, 4) un-clipped samples, or NULL
     float *rew_buf;   // (steps, n)
     uint8_t *done_buf;  // (steps, n)
+    uint8_t *flags_buf; // (steps, n) F_* bits of every step (TimeLimit.truncated = F_TRUNC), or NULL
     int steps;
 };
 
@@ -220,6 +221,7 @@ __global__ void __launch_bounds__(4 * kPolRows, 1) rollout_kernel(const __grid_c
                 const size_t k1 = (size_t)t * (size_t)P.n + (size_t)env;
                 R.rew_buf[k1] = reward;
                 R.done_buf[k1] = (uint8_t)(dn ? 1 : 0);
+                if (R.flags_buf) R.flags_buf[k1] = (uint8_t)fl;
                 if (P.stats) {
                     reward_acc += reward;
                     c_act += 1; c_done += (fl & F_DONE) != 0; c_tr += (fl & F_TRUNC) != 0; c_gp += (fl & F_PASSED) != 0;

@@ -79,6 +79,10 @@ class _QuadGatesBase(_VecEnvBase):
         self._lib = L.load()
         self._vid = L.E2E if self._VARIANT == "e2e" else L.INDI
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type != "cuda":
+            raise L.QuadsimError(f"device {self.device} is not a CUDA device (there is no CPU fallback)")
+        if self.device.index is None:  # "cuda" = the CURRENT device, not ordinal 0
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.reset_rng = reset_rng
 
         # -- race track (`:298-302`)
@@ -111,7 +115,7 @@ class _QuadGatesBase(_VecEnvBase):
         # -- device side
         h = L._vp()
         st = self._lib.qs_create(C.byref(h), self._vid, n, ng, _f(self.gate_pos), _f(self.gate_yaw),
-                                 _f(self.start_pos), self.gates_ahead, self.device.index or 0,
+                                 _f(self.start_pos), self.gates_ahead, self.device.index,
                                  L._vp(torch.cuda.current_stream(self.device).cuda_stream))
         L.check(self._lib, None, st, "qs_create")
         self._h = h
@@ -308,23 +312,28 @@ class _QuadGatesBase(_VecEnvBase):
         return np.frombuffer((C.c_char * max(nbytes, 1)).from_address(p), dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
     def _step_wait_host(self, mode):
-        """NumPy-facing fast path (``reset_rng="device"``): ONE ``qs_step_host`` call -- chunk-pipelined H2D of the
-        actions, step kernel, D2H of obs / reward / done / flags -- into a ring of pinned NumPy arrays.  The returned
-        arrays are recycled after ``obs_buffers`` further steps (SB3 copies them into its rollout buffer within one)."""
+        """NumPy-facing fast path (``reset_rng="device"``): ONE ``qs_step_host_ex`` call -- chunk-pipelined staging + H2D
+        of the caller's action array (float32 or float64, as given), step kernel, D2H of obs / reward / done / flags --
+        into a ring of pinned NumPy arrays; the scan for the ``infos`` quirk happens behind the C ABI as well.  The
+        returned arrays are recycled after ``obs_buffers`` further steps (SB3 copies them into its rollout buffer
+        within one)."""
         n = self.num_envs
         if self._host_ring is None:
             self._host_ring = [{"obs": self._pinned((n, self.state_len), np.float32), "rew": self._pinned((n,), np.float32),
                                 "done": self._pinned((n,), np.uint8), "flags": self._pinned((n,), np.uint8)}
                                for _ in self._obs_ring]
-            self._host_act = self._pinned((n, 4), np.float32)
         k = self._next_slot()
         h = self._host_ring[k]
-        np.copyto(self._host_act, np.asarray(self.actions).reshape(n, 4), casting="unsafe")
+        act = self.actions
+        if not (isinstance(act, np.ndarray) and act.dtype in (np.float32, np.float64) and act.flags.c_contiguous
+                and act.size == 4 * n):
+            act = np.ascontiguousarray(act, dtype=np.float32).reshape(n, 4)
         vp = lambda a: L._vp(a.ctypes.data)
-        self._call("qs_step_host", vp(self._host_act), vp(h["obs"]), vp(h["rew"]), vp(h["done"]), vp(h["flags"]), mode,
-                   L.RESET_DEVICE)
+        info = L.QsStepInfo()
+        self._call("qs_step_host_ex", vp(act), L.F64 if act.dtype == np.float64 else L.F32, vp(h["obs"]), vp(h["rew"]),
+                   vp(h["done"]), vp(h["flags"]), mode, L.RESET_DEVICE, C.byref(info))
         self._ring_stale = True
-        return h["obs"], h["rew"], h["done"].view(np.bool_), h["flags"]
+        return h["obs"], h["rew"], h["done"].view(np.bool_), h["flags"], info
 
     def current_obs_tensor(self):
         """The observations of the current state as a CUDA tensor (N, D): what ``step_tensor`` / ``rollout`` last wrote,
@@ -343,15 +352,14 @@ class _QuadGatesBase(_VecEnvBase):
         self._sync_stream()
         if self.reset_rng == "device":
             mode = self._mode()
-            obs, rewards, dones, flags = self._step_wait_host(mode)
+            obs, rewards, dones, flags, si = self._step_wait_host(mode)
             if mode != L.MODE_PAUSE:
                 self.states = obs
             self.dones, self.last_flags = dones, flags
-            info = {}
-            idx = np.flatnonzero(dones)
-            if idx.size:
-                info["terminal_observation"] = self.states[idx[-1]]
-            if (flags & L.F_TRUNCATED).any():
+            info = {}  # ONE dict aliased N times, like the reference's `[{}] * num_envs` (`:589-594`)
+            if si.last_done_index >= 0:
+                info["terminal_observation"] = self.states[si.last_done_index]
+            if si.any_truncated:
                 info["TimeLimit.truncated"] = True
             return self.states, rewards, dones, [info] * n
         act = np.ascontiguousarray(self.actions, dtype=np.float32).reshape(n, 4)
@@ -412,7 +420,8 @@ class _QuadGatesBase(_VecEnvBase):
         """collect_rollouts on the device (SB3's loop behind `model.learn`, `3D quad race.ipynb:820`): ``steps`` x
         (policy forward -> env step) enqueued back to back, no host round trip.  Returns CUDA tensors
         ``obs (steps+1, N, D)``, ``actions (steps, N, 4)`` (clipped), ``raw_actions (steps, N, 4)`` (un-clipped samples),
-        ``rewards (steps, N)``, ``dones (steps, N)`` (uint8);
+        ``rewards (steps, N)``, ``dones (steps, N)`` (uint8); a caller-supplied ``buffers["flags"]`` (steps, N) uint8
+        also receives every step's ``F_*`` bits (``F_TRUNCATED`` = the reference's ``TimeLimit.truncated``);
         ``obs[0]`` is the observation the rollout started from, ``obs[steps]`` the one the next rollout starts from.
         ``fused``: True = ONE launch of the closed-loop kernel (quads stay in registers for all ``steps``; same results
         bit for bit), False = 2*steps launches, None = fused whenever the shapes fit."""
@@ -431,8 +440,8 @@ class _QuadGatesBase(_VecEnvBase):
         self._call("qs_rollout_fused" if fused else "qs_rollout", policy._h, int(steps), L._vp(buffers["obs"].data_ptr()),
                    L._vp(buffers["actions"].data_ptr()),
                    L._vp(buffers["raw_actions"].data_ptr()) if "raw_actions" in buffers else None,
-                   L._vp(buffers["rewards"].data_ptr()),
-                   L._vp(buffers["dones"].data_ptr()), int(bool(deterministic)))
+                   L._vp(buffers["rewards"].data_ptr()), L._vp(buffers["dones"].data_ptr()),
+                   L._vp(buffers["flags"].data_ptr()) if "flags" in buffers else None, int(bool(deterministic)))
         self._obs_ring[self._ring].copy_(buffers["obs"][steps])
         self._ring_stale = False
         return buffers

@@ -25,6 +25,10 @@ class MlpPolicy:
             raise L.QuadsimError("no CUDA device: the policy only runs on the GPU (there is no CPU fallback)")
         self._lib = L.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type != "cuda":
+            raise L.QuadsimError(f"device {self.device} is not a CUDA device (there is no CPU fallback)")
+        if self.device.index is None:  # "cuda" = the CURRENT device, not ordinal 0
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.weights = [np.ascontiguousarray(w, np.float32) for w in weights]
         self.biases = [np.ascontiguousarray(b, np.float32) for b in biases]
         nl = len(self.weights)
@@ -40,7 +44,7 @@ class MlpPolicy:
             self.std[:self.out_dim] = np.asarray(std, np.float32)
         h = L._vp()
         st = self._lib.qs_policy_create(C.byref(h), self.in_dim, nl - 1, self.hidden, self.out_dim,
-                                        self.device.index or 0, L._vp(torch.cuda.current_stream(self.device).cuda_stream))
+                                        self.device.index, L._vp(torch.cuda.current_stream(self.device).cuda_stream))
         if st != 0:
             raise L.QuadsimError(f"qs_policy_create failed ({st}): {self._lib.qs_policy_last_error(None).decode()}")
         self._h = h

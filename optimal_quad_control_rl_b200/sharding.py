@@ -48,10 +48,17 @@ class ObsAllGather:
 
 
 class ObsPeerGather:
-    """The observation all-gather fused INTO the step kernel: the gather buffer lives in symmetric memory
+    """The observation all-gather fused INTO the step kernel: the gather buffers live in symmetric memory
     (``torch.distributed._symmetric_memory``: every rank's buffer is mapped into every process), each rank's step
-    kernel stores its observation tiles into its own slice of ALL buffers over NVLink while it computes the next
-    tile, and one cross-rank barrier replaces the collective.  Same contents as ``ObsAllGather`` afterwards."""
+    kernel stores its observation tiles into its own slice of ALL ranks' buffers over NVLink while it computes the
+    next tile, and one cross-rank barrier replaces the collective.  Same contents as ``ObsAllGather`` afterwards.
+
+    Protocol (race-free by construction): there are TWO symmetric buffers and consecutive steps alternate between
+    them.  ``gather()`` = one barrier on the current stream: once a rank is past it, every rank's stores of this step
+    have landed.  A rank can only start storing step t+2 (same buffer as step t) after passing the barrier of step
+    t+1, i.e. after every peer has *enqueued past* its own consumers of step t's buffer (stream order: step t,
+    barrier t, consumers of t, step t+1, barrier t+1, ...).  So nobody overwrites a buffer a peer still reads, as long
+    as the consumers run on the stream ``gather()`` was called on."""
 
     def __init__(self, total_envs, obs_len, device, group=None):
         import torch.distributed._symmetric_memory as symm_mem
@@ -59,19 +66,40 @@ class ObsPeerGather:
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         self.first, self.count = shard_range(total_envs, self.rank, self.world)
-        self.buf = symm_mem.empty((total_envs, obs_len), dtype=torch.float32, device=device)
-        self.buf.zero_()
-        self.handle = symm_mem.rendezvous(self.buf, self.group)
-        self.peer_ptrs = [int(p) for r, p in enumerate(self.handle.buffer_ptrs) if r != self.rank]
+        if (self.first * obs_len * 4) % 16:
+            raise ValueError("ObsPeerGather: this rank's slice must start on a 16-byte boundary "
+                             "(first_env * obs_len * 4 % 16 == 0) for the TMA bulk stores into peer memory")
+        self.bufs, self.handles, self.peer_ptrs = [], [], []
+        for _ in range(2):
+            b = symm_mem.empty((total_envs, obs_len), dtype=torch.float32, device=device)
+            b.zero_()
+            h = symm_mem.rendezvous(b, self.group)
+            self.bufs.append(b)
+            self.handles.append(h)
+            self.peer_ptrs.append([int(p) for r, p in enumerate(h.buffer_ptrs) if r != self.rank])
+        self.parity = 0
+        self.env = None
+
+    @property
+    def buf(self):
+        """The buffer the current step writes / the last ``gather()`` returned."""
+        return self.bufs[self.parity]
 
     def attach(self, env):
         """Point ``env``'s step kernel at the peers; its ``obs_out`` must be ``local_slot()``."""
-        env.set_obs_peers(self.peer_ptrs, self.first)
+        self.env = env
+        env.set_obs_peers(self.peer_ptrs[self.parity], self.first)
 
     def local_slot(self):
-        return self.buf[self.first:self.first + self.count]
+        """Where this rank's NEXT step must write its observations (``step_tensor(..., obs_out=local_slot())``)."""
+        return self.bufs[self.parity][self.first:self.first + self.count]
 
     def gather(self):
-        """Wait until every rank's step kernel has finished writing: afterwards ``buf`` holds all observations."""
-        self.handle.barrier()
-        return self.buf
+        """Wait until every rank's step kernel has finished writing; returns the buffer holding all observations of
+        this step and switches the attached env to the other buffer for the next step."""
+        full = self.bufs[self.parity]
+        self.handles[self.parity].barrier()
+        self.parity ^= 1
+        if self.env is not None:
+            self.env.set_obs_peers(self.peer_ptrs[self.parity], self.first)
+        return full

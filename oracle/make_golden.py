@@ -111,6 +111,73 @@ def single_step_inputs(variant, track, seed):
     return ws, tg, sc, act, dist
 
 
+def teacher_set_inputs(variant, track, seed, n=1 << 20):
+    """SURVEY section 8(d)'s teacher-forced parity set at full size: n states -- half from the uniform sampling box,
+    3/8 flying through / past their gate, 1/8 on the ground / bounds / rate thresholds -- with counters around the
+    time limit.  Pure NumPy (PCG64): the same arrays on every machine, so a digest of the reference's answers can be
+    checked on the GPU box where the reference itself is absent."""
+    rng = np.random.default_rng(seed)
+    ng = len(track[1])
+    a, b = n // 2, (3 * n) // 8
+    c = n - a - b
+    ws_a = random_states(variant, a, rng, track)
+    ws_b, tg_b = gate_crossing_states(variant, b, rng, track)
+    ws_c = edge_states(variant, c, rng, track)
+    ws = np.concatenate([ws_a, ws_b, ws_c]).astype(np.float32)
+    tg = np.concatenate([rng.integers(0, ng, a), tg_b, rng.integers(0, ng, c)]).astype(np.int64)
+    sc = rng.integers(0, 1198, n).astype(np.int64)
+    sc[rng.random(n) < 0.03] = 1198
+    sc[rng.random(n) < 0.03] = 1199
+    sc[rng.random(n) < 0.01] = 1500
+    act = rng.uniform(-1, 1, (n, 4)).astype(np.float32)
+    dist = None
+    if variant == "e2e":
+        dr = R.training_disturbance_ranges()
+        dist = rng.uniform(dr[:, 0], dr[:, 1], (n, 6)).astype(np.float32)
+    perm = rng.permutation(n)  # mix the three kinds across warps / tiles
+    return ws[perm], tg[perm], sc[perm], act[perm], (dist[perm] if dist is not None else None)
+
+
+TEACHER_SEED = {"e2e": 2020, "indi": 2021}
+TEACHER_STRIDE = 64  # every 64th env of the reference's float outputs is kept in the digest
+
+
+def sha(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def teacher_reference_step(variant, ws, tg, sc, act, dist, track):
+    """One pause_if_collision step of the UNMODIFIED reference env over the teacher set (no RNG involved)."""
+    n = len(ws)
+    env = R.make_reference_env(variant, n, gates_ahead=1, pause_if_collision=True, track=track)
+    force_state(env, ws, tg, sc, dist)
+    obs0 = env.states.copy()
+    obs, rew, done, _ = env.step(act)
+    return dict(obs0=obs0, obs=obs.copy(), rew=rew.copy(), done=done.copy(), ws=env.world_states.copy(),
+                tg=env.target_gates.copy(), sc=env.step_counts.copy())
+
+
+def make_teacher_digest(variant, n=1 << 20):
+    """2**20-state teacher-forced digest: SHA-256 of the reference's done / target_gate / step_count arrays (bit-exact
+    quantities) plus every 64th row of its float outputs.  ~3 MB per variant instead of ~250 MB."""
+    track = R.zigzag_track() if variant == "e2e" else R.rectangle_track()
+    seed = TEACHER_SEED[variant]
+    ws, tg, sc, act, dist = teacher_set_inputs(variant, track, seed, n)
+    r = teacher_reference_step(variant, ws, tg, sc, act, dist, track)
+    k = TEACHER_STRIDE
+    out = dict(n=np.int64(n), seed=np.int64(seed), stride=np.int64(k),
+               sha_inputs=sha(np.concatenate([ws.ravel(), act.ravel()])), sha_done=sha(r["done"].astype(np.uint8)),
+               sha_tg=sha(r["tg"].astype(np.int64)), sha_sc=sha(r["sc"].astype(np.int64)),
+               n_done=np.int64(r["done"].sum()), n_gate_passed=np.int64((r["tg"] != tg).sum()),
+               obs0=r["obs0"][::k], obs=r["obs"][::k], rew=r["rew"][::k], ws=r["ws"][::k],
+               rew_sum=np.float64(r["rew"].astype(np.float64).sum()))
+    np.savez_compressed(os.path.join(GOLD, f"{variant}_teacher_2p20_digest.npz"), **out)
+    return {kk: (str(v) if isinstance(v, str) else (int(v) if np.ndim(v) == 0 and np.issubdtype(np.asarray(v).dtype, np.integer)
+                                                     else (float(v) if np.ndim(v) == 0 else list(np.shape(v)))))
+            for kk, v in out.items()}
+
+
 # ------------------------------------------------------------------------------------------------ helpers
 def force_state(env, ws, tg, sc, dist):
     env.world_states = ws.copy()
@@ -250,6 +317,26 @@ def make_obs_ga(variant, ga, seed):
     np.savez_compressed(os.path.join(GOLD, f"{variant}_obs_ga{ga}.npz"), **out)
 
 
+def make_obs_offcentre(seed=77):
+    """Disturbance observation 2*(d-lo)/(hi-lo)-1 (`3D quad race.ipynb:414-448`) for NARROW ranges FAR from zero, as a
+    float64 and as a float32 ranges array: a folded d*scale+offset form loses ~1e-3 here."""
+    track = R.zigzag_track()
+    rng = np.random.default_rng(seed)
+    m = 512
+    ws, tg, sc, act, _ = single_step_inputs("e2e", track, seed)
+    ws, tg, sc = ws[:m], tg[:m], sc[:m]
+    ranges = np.array([[10.0, 10.001], [-5.0, -4.99], [0.2, 0.2003], [0, 0], [0, 0], [100.0, 100.01]])
+    dist = rng.uniform(ranges[:, 0], ranges[:, 1], (m, 6)).astype(np.float32)
+    out = dict(in_ws=ws, in_tg=tg, in_sc=sc, in_dist=dist, disturbance_ranges=ranges)
+    for tag, dt in (("f64", np.float64), ("f32", np.float32)):
+        env = R.make_reference_env("e2e", m, gates_ahead=1, track=track, disturbance_ranges=None)
+        env.disturbance_ranges = ranges.astype(dt)
+        force_state(env, ws, tg, sc, dist)
+        out[f"obs_{tag}"] = env.states.copy()
+    np.savez_compressed(os.path.join(GOLD, "e2e_obs_offcentre.npz"), **out)
+    return {k: list(np.shape(v)) for k, v in out.items()}
+
+
 def make_kat():
     G = R.load_reference("e2e")
     st = np.zeros((4, 16), np.float32)
@@ -284,6 +371,15 @@ def main():
     import torch
 
     os.makedirs(GOLD, exist_ok=True)
+    if "--teacher-only" in sys.argv:  # add / refresh the 2**20-state digests without touching the other fixtures
+        with open(os.path.join(GOLD, "MANIFEST.json")) as f:
+            manifest = json.load(f)
+        for variant in ("e2e", "indi"):
+            manifest["files"][f"{variant}_teacher_2p20_digest"] = make_teacher_digest(variant)
+        manifest["files"]["e2e_obs_offcentre"] = make_obs_offcentre()
+        with open(os.path.join(GOLD, "MANIFEST.json"), "w") as f:
+            json.dump(manifest, f, indent=1, sort_keys=True)
+        return
     manifest = dict(generator="oracle/make_golden.py", reference_commit="7aaa3f689e0991c74132274c9f0bb8c72c2ad3a1",
                     numpy=np.__version__, sympy=sympy.__version__, torch=torch.__version__, files={})
     manifest["residual_weights"] = export_residual_weights()
@@ -294,6 +390,8 @@ def main():
         manifest["files"][f"{variant}_traj_n16"] = make_traj(variant, 16, 400, 2, 3, "traj_n16", max_steps=150)
         for ga in (0, 2):
             make_obs_ga(variant, ga, seed + 20 + ga)
+        manifest["files"][f"{variant}_teacher_2p20_digest"] = make_teacher_digest(variant)
+    manifest["files"]["e2e_obs_offcentre"] = make_obs_offcentre()
     with open(os.path.join(GOLD, "MANIFEST.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
     for fn in sorted(os.listdir(GOLD)):

@@ -1,9 +1,11 @@
 """TEST INFRASTRUCTURE — runs the *unmodified* reference notebook cells as the ground truth.
 
-This module only works where ``/root/reference`` is mounted (the build container).  It is used by
-``oracle/make_golden.py`` to freeze golden vectors into ``tests/golden/`` and by the optional
-``tests/test_oracle_vs_reference_live.py`` cross-check.  Nothing on the GPU box imports it and the product
-package never does.
+Reference root, in order: ``$QUADSIM_REFERENCE_ROOT``; ``/root/reference`` (the build container); the staged copy
+``oracle/_ref/reference`` (written by ``stage_reference()`` from ``__graft_entry__.build()`` -- git-ignored, it
+travels to the GPU box with the snapshot like the ``.so`` files next to it, so that ``bench.py`` can time the
+reference's own NumPy ``step()`` on the box's host cores).  Used by ``oracle/make_golden.py`` (golden vectors),
+``tests/test_oracle_vs_reference_live.py`` (live cross-check of the C oracle) and ``bench.py``'s CPU legs.  The
+product package never imports it.
 
 Recipe:
   * E2E  : ``3D quad race.ipynb`` code cells 2 (sympy EoM -> f_func), 4 (residual MLPs), 6 (Quadcopter3DGates)
@@ -20,13 +22,43 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("QUADSIM_REFERENCE_ROOT", "/root/reference")
 E2E_NOTEBOOK = "3D quad race.ipynb"
 INDI_NOTEBOOK = "3D quad race INDI inner loop.ipynb"
+_HERE = os.path.dirname(os.path.abspath(__file__))
+STAGED_ROOT = os.path.join(_HERE, "_ref", "reference")
+_STAGED_FILES = (E2E_NOTEBOOK, INDI_NOTEBOOK, os.path.join("NNDroneModel", "thrust_model.pt"),
+                 os.path.join("NNDroneModel", "moment_model.pt"))
+
+
+def _find_root():
+    cands = [os.environ.get("QUADSIM_REFERENCE_ROOT"), "/root/reference", STAGED_ROOT]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, E2E_NOTEBOOK)):
+            return c
+    return cands[0] or "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, E2E_NOTEBOOK))
+
+
+def stage_reference(src="/root/reference") -> bool:
+    """Copy the files the two env notebooks need (the notebooks themselves + NNDroneModel/*.pt) from the mounted
+    reference into oracle/_ref/reference, byte for byte.  oracle/_ref is git-ignored: nothing of the reference enters
+    the repository history.  Returns False (and changes nothing) where the reference is not mounted."""
+    import shutil
+
+    if not os.path.isfile(os.path.join(src, E2E_NOTEBOOK)):
+        return False
+    for rel in _STAGED_FILES:
+        dst = os.path.join(STAGED_ROOT, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(os.path.join(src, rel), dst)
+        os.chmod(dst, 0o644)
+    return True
 
 
 class _Box:

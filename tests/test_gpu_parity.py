@@ -251,6 +251,42 @@ def test_step_vs_oracle(variant, n, tracks):
     assert done.sum() > 0 or n < 100
 
 
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_disturbance_obs_narrow_offcentre_ranges(dtype, tracks):
+    """2*(d-lo)/(hi-lo)-1 for ranges like [10, 10.001] (`3D quad race.ipynb:414-448`): the kernel subtracts first, like the
+    reference, in the precision of the ranges array (a folded d*scale+offset form is off by ~1e-3 here)."""
+    g = golden("e2e_obs_offcentre")
+    dt = np.float64 if dtype == "f64" else np.float32
+    env = make_env("e2e", len(g["in_ws"]), tracks, ranges=g["disturbance_ranges"].astype(dt))
+    obs = force(env, g["in_ws"], g["in_tg"], g["in_sc"], g["in_dist"])
+    assert_close(obs, g[f"obs_{dtype}"], "obs")
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_teacher_set_2p20_digest(variant, tracks):
+    """SURVEY section 8(d)'s full-size teacher-forced set through the CUDA path: 2**20 states incl. the near-threshold
+    generators; done / target_gate / step_count hash to the REFERENCE's own arrays (digest frozen from the unmodified
+    notebook cells by oracle/make_golden.py --teacher-only), every 64th float row within the 1e-5 gate of the reference's."""
+    from oracle import make_golden as MG
+    g = golden(f"{variant}_teacher_2p20_digest")
+    n, k = int(g["n"]), int(g["stride"])
+    ws, tg, sc, act, dist = MG.teacher_set_inputs(variant, tracks[variant], int(g["seed"]), n)
+    assert MG.sha(np.concatenate([ws.ravel(), act.ravel()])) == str(g["sha_inputs"]), "input generator drifted"
+    env = make_env(variant, n, tracks, pic=True, ranges=MG.R.training_disturbance_ranges() if variant == "e2e" else None)
+    obs0 = force(env, ws, tg, sc, dist)
+    assert_close(obs0[::k], g["obs0"], "obs before")
+    obs, rew, done, _ = env.step(act)
+    assert MG.sha(done.astype(np.uint8)) == str(g["sha_done"])
+    assert MG.sha(env.target_gates.astype(np.int64)) == str(g["sha_tg"])
+    assert MG.sha(env.step_counts.astype(np.int64)) == str(g["sha_sc"])
+    w1 = env.world_states
+    np.testing.assert_array_equal(w1[::k, 0:3], g["ws"][:, 0:3])
+    assert_close(w1[::k], g["ws"], "world_states")
+    assert_close(obs[::k], g["obs"], "obs")
+    assert_close(rew[::k], g["rew"], "reward")
+    print(variant, "max scaled err CUDA vs reference (every 64th of 2**20):", float(scaled_err(w1[::k], g["ws"]).max()))
+
+
 # ------------------------------------------------------------------------------------------------ size-independent properties
 @pytest.mark.parametrize("variant", VARIANTS)
 def test_properties_full_size(variant, tracks):

@@ -5,6 +5,12 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+def PK():
+    """the reference's policy_kwargs (`3D quad race.ipynb:784`)"""
+    import torch
+    return dict(activation_fn=torch.nn.ReLU, net_arch=[dict(pi=[120, 120, 120], vf=[120, 120, 120])], log_std_init=0)
+
+
 def gae_reference(rew, val, done, gamma, lam):
     """stable_baselines3.common.buffers.RolloutBuffer.compute_returns_and_advantage, restated:
     next_non_terminal comes from the done flag of the SAME step (SB3 stores episode_starts of the next step)."""
@@ -46,7 +52,7 @@ def test_ppo_short_run_improves_reward(tracks):
     import optimal_quad_control_rl_b200 as Q
     gp, gy, sp = tracks["indi"]
     env = Q.Quadcopter3DGatesINDI(4096, gp, gy, sp, gates_ahead=1, reset_rng="device", seed=0)
-    ppo = Q.PPO(env, n_steps=128, batch_size=16384, n_epochs=4, seed=0)
+    ppo = Q.PPO("MlpPolicy", env, policy_kwargs=PK(), n_steps=128, batch_size=16384, n_epochs=4, gamma=0.999, seed=0)
     b = ppo.collect_rollouts()
     with torch.no_grad():  # before any update: new log-prob == stored log-prob
         lp = ppo._log_prob(b["obs"][:4].reshape(-1, env.state_len), b["raw_actions"][:4].reshape(-1, 4))
@@ -73,7 +79,7 @@ def test_ppo_update_survives_degenerate_samples(tracks):
     gp, gy, sp = tracks["e2e"]
     env = Q.Quadcopter3DGates(2048, gp, gy, sp, gates_ahead=1, reset_rng="device", seed=1)
     env.disturbance_ranges = Q.training_disturbance_ranges()
-    ppo = Q.PPO(env, n_steps=32, batch_size=8192, n_epochs=2, seed=1)
+    ppo = Q.PPO("MlpPolicy", env, policy_kwargs=PK(), n_steps=32, batch_size=8192, n_epochs=2, gamma=0.999, seed=1)
     orig = env.rollout
 
     def poisoned(actor, steps, buffers=None, **kw):
@@ -104,7 +110,7 @@ def test_ppo_checkpoint_round_trip_and_controller_export(tmp_path, tracks):
     import optimal_quad_control_rl_b200 as Q
     gp, gy, sp = tracks["indi"]
     env = Q.Quadcopter3DGatesINDI(1024, gp, gy, sp, gates_ahead=1, reset_rng="device", seed=2)
-    ppo = Q.PPO(env, n_steps=16, batch_size=4096, n_epochs=1, seed=2)
+    ppo = Q.PPO("MlpPolicy", env, policy_kwargs=PK(), n_steps=16, batch_size=4096, n_epochs=1, gamma=0.999, seed=2)
     ppo.learn(iterations=2)
     path = ppo.save(str(tmp_path / "models" / "indi" / str(ppo.num_timesteps)))
     env2 = Q.Quadcopter3DGatesINDI(1024, gp, gy, sp, gates_ahead=1, reset_rng="device", seed=2)
@@ -153,3 +159,160 @@ def test_trajectory_log_over_the_gpu_env(tmp_path, tracks):
     r = env.render()
     assert set(r) == {"x", "y", "z", "vx", "vy", "vz", "phi", "theta", "psi", "p", "q", "r", "T", "u1", "u2", "u3", "u4"}
     env.close()
+
+
+# ------------------------------------------------------------------------------------------------ SB3 drop-in (row f2)
+def test_reference_training_cell_runs_with_only_the_import_changed(tmp_path, tracks):
+    """The reference's training cell (`3D quad race.ipynb:765-795`) and its train() loop (`:816-823`), statement for
+    statement, with `from stable_baselines3 import PPO` / `VecMonitor` replaced by this package's.  num_envs / n_steps are
+    the reference's (100 x 1000 would take minutes through the host loop: shortened to 100 x 20, batch 500)."""
+    import torch
+    from optimal_quad_control_rl_b200 import PPO, VecMonitor, Quadcopter3DGates
+    gate_pos, gate_yaw, start_pos = tracks["e2e"]
+    models_dir, log_dir = str(tmp_path / "models" / "E2E"), str(tmp_path / "logs" / "E2E")
+    np.random.seed(0)
+    env = Quadcopter3DGates(num_envs=100, gates_pos=gate_pos, gate_yaw=gate_yaw, start_pos=start_pos, gates_ahead=1)
+    test_env = Quadcopter3DGates(num_envs=10, gates_pos=gate_pos, gate_yaw=gate_yaw, start_pos=start_pos, gates_ahead=1,
+                                 pause_if_collision=True)
+    env = VecMonitor(env)
+    disturbance_ranges = np.array([[-0.03, 0.03], [-0.03, 0.03], [-0.01, 0.01], [0, 0], [0, 0], [-0.5, 0.5]])
+    env.venv.disturbance_ranges = disturbance_ranges
+    test_env.disturbance_ranges = disturbance_ranges
+    policy_kwargs = dict(activation_fn=torch.nn.ReLU, net_arch=[dict(pi=[120, 120, 120], vf=[120, 120, 120])], log_std_init=0)
+    model = PPO("MlpPolicy", env, policy_kwargs=policy_kwargs, verbose=0, tensorboard_log=log_dir, n_steps=20, batch_size=500,
+                n_epochs=10, gamma=0.999)
+    print(model.policy)
+    assert model.num_timesteps == 0 and model.rollout == "host" and model.bootstrap == "sb3_a8"
+    test_env.reset()
+    actions, _ = model.predict(test_env.states, deterministic=False)      # animate_policy's body (`:800-806`)
+    states, rewards, dones, infos = test_env.step(actions)
+    assert states.shape == (10, 24) and set(test_env.render()) >= {"x", "psi", "w4", "u1"}
+    log_name = "zigzag"
+    TIMESTEPS = model.n_steps * env.num_envs * 2                            # train() (`:816-823`), 2 rollouts per save
+    for i in range(2):
+        model.learn(total_timesteps=TIMESTEPS, reset_num_timesteps=False, tb_log_name=log_name)
+        time_steps = model.num_timesteps
+        model.save(models_dir + '/' + log_name + '/' + str(time_steps))
+    assert model.num_timesteps == 2 * TIMESTEPS == 8000
+    import os
+    assert os.path.isfile(models_dir + "/zigzag/8000.zip")
+    assert os.path.isfile(os.path.join(log_dir, "zigzag_1", "progress.jsonl"))
+    loaded = PPO.load(models_dir + "/zigzag/8000.zip")                     # `:3985-3995`: no env
+    network = list(loaded.policy.mlp_extractor.policy_net) + [loaded.policy.action_net]
+    assert [m.out_features for m in network if hasattr(m, "out_features")] == [120, 120, 120, 4]
+    network_std = loaded.policy.log_std.exp().cpu().detach().numpy()
+    assert network_std.shape == (4,) and str(loaded.policy.action_dist).startswith("DiagGaussian")
+    a1, _ = model.predict(states, deterministic=True)
+    a2, _ = loaded.predict(states, deterministic=True)
+    np.testing.assert_array_equal(a1, a2)
+    h = model.history
+    assert len(h) == 4 and all(np.isfinite(r["pg_loss"]) and np.isfinite(r["ep_rew_mean"]) for r in h)
+
+
+def _fake_sb3_collect(env, policy_fn, value_fn, n_steps, gamma):
+    """SB3 2.1 ``OnPolicyAlgorithm.collect_rollouts`` restated with NumPy buffers (test double of the real caller):
+    obs are read from ``_last_obs`` AFTER ``env.step``; infos are used the way VecMonitor + SB3 use them."""
+    n = env.num_envs
+    last_obs = env.reset()
+    buf = {"obs": [], "actions": [], "rewards": [], "dones": []}
+    for t in range(n_steps):
+        actions = policy_fn(last_obs)
+        clipped = np.clip(actions, -1, 1)
+        new_obs, rewards, dones, infos = env.step(clipped)
+        assert new_obs.dtype == np.float32 and rewards.dtype == np.float32 and dones.dtype == np.bool_ and len(infos) == n
+        rewards = rewards.copy()
+        for idx, done in enumerate(dones):
+            if done and infos[idx].get("terminal_observation") is not None and infos[idx].get("TimeLimit.truncated", False):
+                rewards[idx] += gamma * value_fn(infos[idx]["terminal_observation"][None])[0]
+        buf["obs"].append(last_obs.copy())        # rollout_buffer.add(self._last_obs, ...): AFTER the step
+        buf["actions"].append(actions); buf["rewards"].append(rewards); buf["dones"].append(dones.copy())
+        last_obs = new_obs
+    return {k: np.stack(v) for k, v in buf.items()}, last_obs
+
+
+@pytest.mark.parametrize("reset_rng", ["numpy", "device"])
+def test_fake_sb3_collect_rollouts_over_the_numpy_facing_env(reset_rng, tracks):
+    """SB3-shaped driver over the NumPy-facing GPU env: the observation handed out by step t must still be intact when
+    the caller stores it after step t+1 (obs_buffers=2 pinned ring), infos behave like the reference's aliased dict,
+    VecMonitor can copy them, float64 actions are accepted; in numpy-RNG mode the whole rollout matches the CPU oracle
+    env driven by the same loop."""
+    import optimal_quad_control_rl_b200 as Q
+    from oracle import c_oracle as O
+    gp, gy, sp = tracks["e2e"]
+    n, T = 256, 40
+    rng = np.random.default_rng(3)
+    Wp = rng.normal(0, 0.3, (24, 4))
+    policy_fn = lambda obs: (np.tanh(obs @ Wp) + rng.normal(0, 0.5, (len(obs), 4)))      # float64 actions on purpose
+    value_fn = lambda obs: obs[:, :3].sum(1).astype(np.float32)
+    env = Q.Quadcopter3DGates(n, gp, gy, sp, gates_ahead=1, reset_rng=reset_rng, seed=5, obs_buffers=2)
+    env.disturbance_ranges = Q.training_disturbance_ranges()
+    env.max_steps = 15                                                                    # time-outs happen
+    np.random.seed(11)
+    mon = Q.VecMonitor(env)
+    seen = []
+    inner_step = mon.step
+
+    def spy_step(a):                                                                      # keep what the env handed out
+        out = inner_step(a)
+        seen.append((out[0], out[0].copy()))
+        return out
+    mon.step = spy_step
+    buf, last = _fake_sb3_collect(mon, policy_fn, value_fn, T, 0.999)
+    # (1) every observation array survived until it was stored one step later
+    for t in range(len(seen) - 1):
+        np.testing.assert_array_equal(buf["obs"][t + 1], seen[t][1])
+    assert buf["dones"].sum() > n and mon.episode_count == buf["dones"].sum()
+    if reset_rng == "numpy":  # (2) the same loop over the CPU oracle env, same np.random stream
+        rng = np.random.default_rng(3)
+        Wp2 = rng.normal(0, 0.3, (24, 4))
+        policy2 = lambda obs: (np.tanh(obs @ Wp2) + rng.normal(0, 0.5, (len(obs), 4)))
+        ora = O.OracleEnv("e2e", n, gp, gy, sp, gates_ahead=1)
+        ora.disturbance_ranges = Q.training_disturbance_ranges()
+        ora.max_steps = 15
+        np.random.seed(11)
+        ref, _ = _fake_sb3_collect(Q.VecMonitor(ora), policy2, value_fn, T, 0.999)
+        np.testing.assert_array_equal(buf["dones"], ref["dones"])
+        np.testing.assert_allclose(buf["obs"], ref["obs"], rtol=2e-4, atol=2e-4)
+        np.testing.assert_allclose(buf["rewards"], ref["rewards"], rtol=2e-4, atol=2e-3)
+    env.close()
+
+
+def test_device_rollout_a8_bootstrap_and_host_rollout_agree_on_semantics(tracks):
+    """bootstrap='sb3_a8' on the device path: rewards of the buffer == rewards of bootstrap='none' + the NumPy
+    restatement of SB3's loop over the aliased infos, on the very same rollout."""
+    import torch
+    import optimal_quad_control_rl_b200 as Q
+    from optimal_quad_control_rl_b200.ppo import a8_bootstrap_
+    gp, gy, sp = tracks["indi"]
+    env = Q.Quadcopter3DGatesINDI(512, gp, gy, sp, gates_ahead=1, reset_rng="device", seed=9)
+    env.max_steps = 20
+    ppo = Q.PPO("MlpPolicy", env, policy_kwargs=PK(), n_steps=48, batch_size=4096, n_epochs=1, gamma=0.999, seed=3,
+                bootstrap="sb3_a8")
+    assert ppo.rollout == "device"
+    b = ppo.collect_rollouts()
+    fl, dn = b["flags"].cpu().numpy(), b["dones"].cpu().numpy().astype(bool)
+    assert ((fl & 2) != 0).any() and (((fl & 1) != 0) == dn).all()
+    # recompute from the raw pieces: the device rewards minus the bootstrap must be what the env returned
+    obs_next = b["obs"][1:].cpu().numpy()
+    with torch.no_grad():
+        V = lambda o: ppo._values(torch.as_tensor(o, device=ppo.device)).cpu().numpy()
+    add = np.zeros_like(fl, dtype=np.float32)
+    for t in range(48):                                   # SB3's loop over the reference's aliased infos
+        info = {}
+        idx = np.flatnonzero(dn[t])
+        if idx.size:
+            info["terminal_observation"] = obs_next[t, idx[-1]]
+        if ((fl[t] & 2) != 0).any():
+            info["TimeLimit.truncated"] = True
+        for i in idx:
+            if info.get("terminal_observation") is not None and info.get("TimeLimit.truncated", False):
+                add[t, i] = 0.999 * V(info["terminal_observation"][None])[0]
+    env2 = Q.Quadcopter3DGatesINDI(512, gp, gy, sp, gates_ahead=1, reset_rng="device", seed=9)
+    env2.max_steps = 20
+    plain = Q.PPO("MlpPolicy", env2, policy_kwargs=PK(), n_steps=48, batch_size=4096, n_epochs=1, gamma=0.999, seed=3,
+                  bootstrap="none")
+    b2 = plain.collect_rollouts()
+    assert torch.equal(b2["dones"], b["dones"]) and torch.equal(b2["obs"], b["obs"])
+    np.testing.assert_allclose(b["rewards"].cpu().numpy(), b2["rewards"].cpu().numpy() + add, rtol=1e-5, atol=1e-5)
+    assert np.abs(add).sum() > 0
+    env.close(); env2.close()

@@ -166,3 +166,38 @@ def test_trajectory_free_running_report(variant, tracks):
             first_bad = t
     print(f"{variant}: free-running first step over 1e-5: {first_bad}")
     assert first_bad is None or first_bad >= 20
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_teacher_set_2p20_digest(variant, tracks):
+    """The full-size teacher-forced set of SURVEY section 8(d) (2**20 states incl. the adversarial generators): the
+    oracle's done / target_gate / step_count arrays hash to the reference's, and every 64th row of its float outputs
+    is within the gate of the reference's (digest frozen by oracle/make_golden.py --teacher-only)."""
+    from oracle import make_golden as MG
+    g = golden(f"{variant}_teacher_2p20_digest")
+    n, k = int(g["n"]), int(g["stride"])
+    track = tracks[variant]
+    ws, tg, sc, act, dist = MG.teacher_set_inputs(variant, track, int(g["seed"]), n)
+    assert MG.sha(np.concatenate([ws.ravel(), act.ravel()])) == str(g["sha_inputs"]), "input generator drifted"
+    env = make_env(variant, n, tracks, pic=True, ranges=MG.R.training_disturbance_ranges() if variant == "e2e" else None)
+    env.force(ws, tg, sc, dist)
+    assert_close(env.states[::k], g["obs0"], "obs before")
+    obs, rew, done, _ = env.step(act)
+    assert MG.sha(done.astype(np.uint8)) == str(g["sha_done"])
+    assert MG.sha(env.target_gates.astype(np.int64)) == str(g["sha_tg"])
+    assert MG.sha(env.step_counts.astype(np.int64)) == str(g["sha_sc"])
+    np.testing.assert_array_equal(env.world_states[::k, 0:3], g["ws"][:, 0:3])
+    assert_close(env.world_states[::k], g["ws"], "world_states")
+    assert_close(obs[::k], g["obs"], "obs")
+    assert_close(rew[::k], g["rew"], "reward")
+    assert int(done.sum()) == int(g["n_done"]) > n // 20
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_disturbance_obs_narrow_offcentre_ranges(dtype, tracks):
+    """2*(d-lo)/(hi-lo)-1 for ranges like [10, 10.001]: subtract first, in the dtype of the ranges array."""
+    g = golden("e2e_obs_offcentre")
+    dt = np.float64 if dtype == "f64" else np.float32
+    env = make_env("e2e", len(g["in_ws"]), tracks, ranges=g["disturbance_ranges"].astype(dt))
+    env.force(g["in_ws"], g["in_tg"], g["in_sc"], g["in_dist"])
+    assert_close(env.states, g[f"obs_{dtype}"], "obs")

@@ -9,7 +9,8 @@ amp = "--amp" in sys.argv
 gp, gy, sp = Q.zigzag_track()
 env = Q.Quadcopter3DGates(65536, gp, gy, sp, gates_ahead=1, reset_rng="device", seed=0)
 env.disturbance_ranges = Q.training_disturbance_ranges()
-ppo = Q.PPO(env, n_steps=128, batch_size=1 << 18, n_epochs=2, amp=amp)
+pk = dict(activation_fn=torch.nn.ReLU, net_arch=[dict(pi=[120, 120, 120], vf=[120, 120, 120])], log_std_init=0)
+ppo = Q.PPO("MlpPolicy", env, policy_kwargs=pk, n_steps=128, batch_size=1 << 18, n_epochs=2, gamma=0.999, amp=amp, update="fused" if "--fused" in sys.argv else "torch")
 ppo.collect_rollouts(); ppo.train(); torch.cuda.synchronize()
 import time
 t0 = time.perf_counter(); ppo.collect_rollouts(); torch.cuda.synchronize(); t1 = time.perf_counter()
