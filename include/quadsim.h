@@ -233,6 +233,41 @@ int qs_rollout_fused(qs_env *env, qs_policy *policy, int steps, float *obs_buf, 
 int qs_gae(const float *rew_dev, const float *val_dev, const uint8_t *done_dev, float *adv_dev, float *ret_dev, int64_t n,
            int steps, float gamma, float lambda, void *stream);
 
+/* ---- PPO update on the tensor cores (row f2) ------------------------------------------------------------------
+ * What SB3's `PPO.train()` does for the reference's configuration (`3D quad race.ipynb:784-795`: MlpPolicy with separate
+ * pi / vf networks obs -> h -> h -> h -> {4 | 1}, ReLU, free log_std; clipped surrogate + vf_coef * value MSE - ent_coef *
+ * entropy; per-minibatch advantage normalisation; clip_grad_norm_; Adam eps 1e-5) as hand-written sm_100a kernels: one
+ * fused forward + loss + backward kernel for both networks (tcgen05, weight gradients accumulated in TMEM), a reduction
+ * and an Adam kernel per minibatch (csrc/quadsim_train.cuh).  Float32 master parameters and Adam moments live in the
+ * handle; layers are exchanged in torch layout: W (out, in) row-major, b (out); layer 0..2 hidden, 3 = output. */
+typedef struct qs_trainer qs_trainer;
+typedef struct {
+    float learning_rate, beta1, beta2, eps;      /* Adam (SB3: 3e-4, 0.9, 0.999, 1e-5) */
+    float clip_range, vf_coef, ent_coef, max_grad_norm;
+    float obs_limit, act_limit;                  /* sanitising clamps of the learner's inputs (see ppo.py) */
+    int32_t normalize_advantage;
+    int32_t reserved;
+} qs_train_hyper;
+int qs_trainer_create(qs_trainer **out, int in_dim, int hidden_dim, int device, void *stream);
+int qs_trainer_destroy(qs_trainer *t);
+const char *qs_trainer_last_error(const qs_trainer *t);
+int qs_trainer_set_stream(qs_trainer *t, void *stream);
+int qs_trainer_set_layer(qs_trainer *t, int net /* 0 policy, 1 value */, int layer, const float *W, const float *b);
+int qs_trainer_get_layer(qs_trainer *t, int net, int layer, float *W, float *b);
+int qs_trainer_set_log_std(qs_trainer *t, const float *log_std4);
+int qs_trainer_get_log_std(qs_trainer *t, float *log_std4);
+int qs_trainer_reset_optimizer(qs_trainer *t);
+/* one minibatch of `rows` samples (idx_dev: int64 indices into the flat rollout buffers, or NULL for 0..rows-1); all
+ * pointers are device pointers; apply != 0 also runs the optimizer step.  Asynchronous on the trainer's stream. */
+int qs_trainer_minibatch(qs_trainer *t, const int64_t *idx_dev, int64_t rows, const float *obs_dev, const float *raw_act_dev,
+                         const float *old_logp_dev, const float *adv_dev, const float *ret_dev, const float *weight_dev,
+                         const qs_train_hyper *hyper, int apply);
+int qs_trainer_get_grad(qs_trainer *t, int net, int layer, float *W, float *b, float *log_std4);
+int qs_trainer_get_stats(qs_trainer *t, float *out8, int reset);
+/* hand the updated policy network (BF16 blob + std) to the device actor, device to device */
+int qs_trainer_publish(qs_trainer *t, qs_policy *policy);
+uint64_t qs_trainer_launch_count(const qs_trainer *t);
+
 #ifdef __cplusplus
 }
 #endif

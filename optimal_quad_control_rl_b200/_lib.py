@@ -33,6 +33,13 @@ class QsStepInfo(C.Structure):
 
 F32, F64 = 0, 1
 
+
+class QsTrainHyper(C.Structure):
+    _fields_ = [("learning_rate", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("clip_range", C.c_float), ("vf_coef", C.c_float), ("ent_coef", C.c_float), ("max_grad_norm", C.c_float),
+                ("obs_limit", C.c_float), ("act_limit", C.c_float), ("normalize_advantage", C.c_int32),
+                ("reserved", C.c_int32)]
+
 # name -> (restype, argtypes); every symbol include/quadsim.h declares
 SIGNATURES = {
     "qs_state_len": (C.c_int, [C.c_int]),
@@ -81,6 +88,20 @@ SIGNATURES = {
     "qs_rollout": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "qs_rollout_fused_supported": (C.c_int, [_vp, _vp]),
     "qs_rollout_fused": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
+    "qs_trainer_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, _vp]),
+    "qs_trainer_destroy": (C.c_int, [_vp]),
+    "qs_trainer_last_error": (C.c_char_p, [_vp]),
+    "qs_trainer_set_stream": (C.c_int, [_vp, _vp]),
+    "qs_trainer_set_layer": (C.c_int, [_vp, C.c_int, C.c_int, _fp, _fp]),
+    "qs_trainer_get_layer": (C.c_int, [_vp, C.c_int, C.c_int, _fp, _fp]),
+    "qs_trainer_set_log_std": (C.c_int, [_vp, _fp]),
+    "qs_trainer_get_log_std": (C.c_int, [_vp, _fp]),
+    "qs_trainer_reset_optimizer": (C.c_int, [_vp]),
+    "qs_trainer_minibatch": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(QsTrainHyper), C.c_int]),
+    "qs_trainer_get_grad": (C.c_int, [_vp, C.c_int, C.c_int, _fp, _fp, _fp]),
+    "qs_trainer_get_stats": (C.c_int, [_vp, _fp, C.c_int]),
+    "qs_trainer_publish": (C.c_int, [_vp, _vp]),
+    "qs_trainer_launch_count": (C.c_uint64, [_vp]),
     "qs_gae": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_float, C.c_float, _vp]),
 }
 

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libquadsim.so")
 SOURCES = [os.path.join(CSRC, "quadsim_capi.cu")]
-HEADERS = [os.path.join(CSRC, h) for h in ("quadsim_kernels.cuh", "quadsim_policy.cuh", "quadsim_rollout.cuh")] + \
+HEADERS = [os.path.join(CSRC, h) for h in ("quadsim_kernels.cuh", "quadsim_policy.cuh", "quadsim_rollout.cuh", "quadsim_train.cuh")] + \
           [os.path.join(ROOT, "include", "quadsim.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -4,6 +4,7 @@
 #include "quadsim_kernels.cuh"
 #include "quadsim_policy.cuh"
 #include "quadsim_rollout.cuh"
+#include "quadsim_train.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -948,6 +949,280 @@ int qs_gae(const float *rew_dev, const float *val_dev, const uint8_t *done_dev, 
     qs::gae_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rew_dev, val_dev, done_dev, adv_dev, ret_dev, n,
                                                                                  steps, gamma, lambda);
     return cudaGetLastError() == cudaSuccess ? QS_OK : QS_ERR_CUDA;
+}
+
+
+// ================================================================================================ PPO update (row f2)
+// SB3's PPO.train() for the reference's configuration as three kernels per minibatch (quadsim_train.cuh).
+struct qs_trainer {
+    int device = 0, in_dim = 0, k1 = 0, hidden = 0, n_ctas = 0, nf = 0;
+    cudaStream_t stream = nullptr;
+    float *param = nullptr, *m = nullptr, *v = nullptr, *grad = nullptr;  // (2*nf + 4): policy net, value net, log_std
+    unsigned char *w_pi = nullptr, *w_vf = nullptr;                       // BF16 UMMA-layout blobs
+    float *partial = nullptr, *stats = nullptr;
+    double *mb = nullptr;  // [0..2] minibatch statistics, [3] squared gradient norm
+    std::vector<float> h_param;
+    bool dirty = true;     // host parameters changed: upload + re-pack before the next minibatch
+    uint64_t step = 0, launches = 0;
+    size_t smem = 0;
+    std::string err;
+};
+static std::string g_trainer_create_error;
+static int tfail(qs_trainer *t, int code, const char *msg) {
+    if (t) t->err = msg; else g_trainer_create_error = msg;
+    return code;
+}
+#define QS_TCUDA(t, call)                                                                      \
+    do {                                                                                       \
+        cudaError_t _c = (call);                                                               \
+        if (_c != cudaSuccess) {                                                               \
+            (t)->err = std::string(#call) + ": " + cudaGetErrorString(_c);                     \
+            return QS_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+const char *qs_trainer_last_error(const qs_trainer *t) { return t ? t->err.c_str() : g_trainer_create_error.c_str(); }
+uint64_t qs_trainer_launch_count(const qs_trainer *t) { return t ? t->launches : 0; }
+
+// position of layer `layer` (0..3) element (out, in) inside a network's padded parameter block; bias = the column
+// that multiplies the constant-1 input (in_dim for layer 0, unit 127 afterwards); the output layer is stored transposed
+static size_t tr_index(const qs_trainer *t, int layer, int out, int in) {
+    const int w1 = qs::tr_w1_floats(t->k1), wh = qs::tr_wh_floats();
+    if (layer == 0) return (size_t)out * t->k1 + in;
+    if (layer < 3) return (size_t)w1 + (size_t)(layer - 1) * wh + (size_t)out * qs::kPolHidden + in;
+    return (size_t)w1 + 2 * (size_t)wh + (size_t)in * qs::kPolOut + out;
+}
+
+int qs_trainer_create(qs_trainer **out, int in_dim, int hidden_dim, int device, void *stream) {
+    if (!out) return tfail(nullptr, QS_ERR_ARG, "qs_trainer_create: out is NULL");
+    *out = nullptr;
+    if (in_dim < 1 || in_dim > 63) return tfail(nullptr, QS_ERR_ARG, "qs_trainer_create: in_dim must be 1..63");
+    if (hidden_dim < 1 || hidden_dim > qs::kPolOnes) return tfail(nullptr, QS_ERR_ARG, "qs_trainer_create: hidden_dim must be 1..127");
+    qs_trainer *t = new (std::nothrow) qs_trainer();
+    if (!t) return tfail(nullptr, QS_ERR_NOMEM, "qs_trainer_create: out of host memory");
+    t->device = device; t->in_dim = in_dim; t->hidden = hidden_dim; t->k1 = (in_dim + 1 + 15) / 16 * 16;
+    t->stream = (cudaStream_t)stream;
+    t->nf = qs::tr_net_floats(t->k1);
+    auto bail = [&](cudaError_t c, const char *what) {
+        g_trainer_create_error = std::string(what) + ": " + cudaGetErrorString(c);
+        qs_trainer_destroy(t);
+        return (int)QS_ERR_CUDA;
+    };
+    cudaError_t c;
+    if ((c = cudaSetDevice(device)) != cudaSuccess) return bail(c, "cudaSetDevice");
+    int sms = 0, smem_max = 0;
+    if ((c = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return bail(c, "cudaDeviceGetAttribute");
+    if ((c = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)) != cudaSuccess) return bail(c, "cudaDeviceGetAttribute");
+    t->smem = qs::train_smem_bytes(t->k1);
+    if (t->smem > (size_t)smem_max) { g_trainer_create_error = "training tile does not fit in shared memory"; qs_trainer_destroy(t); return QS_ERR_ARG; }
+    t->n_ctas = sms & ~1;  // even: half the CTAs own the policy network, half the value network
+    const size_t np = 2 * (size_t)t->nf + 4, wb = qs::policy_weight_bytes(t->k1, 3);
+    t->h_param.assign(np, 0.0f);
+    for (int net = 0; net < 2; ++net)  // the rows that re-emit the constant 1 of the bias folding
+        for (int l = 0; l < 3; ++l) t->h_param[(size_t)net * t->nf + tr_index(t, l, qs::kPolOnes, l == 0 ? in_dim : qs::kPolOnes)] = 1.0f;
+    if ((c = cudaMalloc(&t->param, np * 4)) != cudaSuccess || (c = cudaMalloc(&t->m, np * 4)) != cudaSuccess ||
+        (c = cudaMalloc(&t->v, np * 4)) != cudaSuccess || (c = cudaMalloc(&t->grad, np * 4)) != cudaSuccess ||
+        (c = cudaMalloc(&t->w_pi, wb)) != cudaSuccess || (c = cudaMalloc(&t->w_vf, wb)) != cudaSuccess ||
+        (c = cudaMalloc(&t->partial, (size_t)t->n_ctas * (t->nf + qs::kTrStats) * 4)) != cudaSuccess ||
+        (c = cudaMalloc(&t->stats, 8 * 4)) != cudaSuccess || (c = cudaMalloc(&t->mb, 4 * 8)) != cudaSuccess)
+        return bail(c, "cudaMalloc");
+    cudaMemset(t->m, 0, np * 4); cudaMemset(t->v, 0, np * 4); cudaMemset(t->grad, 0, np * 4); cudaMemset(t->stats, 0, 32);
+    cudaMemset(t->w_pi, 0, wb); cudaMemset(t->w_vf, 0, wb);
+    if ((c = cudaFuncSetAttribute((const void *)qs::ppo_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->smem)) != cudaSuccess)
+        return bail(c, "cudaFuncSetAttribute(train smem)");
+    if ((c = cudaDeviceSynchronize()) != cudaSuccess) return bail(c, "cudaDeviceSynchronize");
+    *out = t;
+    return QS_OK;
+}
+
+int qs_trainer_destroy(qs_trainer *t) {
+    if (!t) return QS_OK;
+    cudaSetDevice(t->device);
+    if (t->stream) cudaStreamSynchronize(t->stream); else cudaDeviceSynchronize();
+    cudaFree(t->param); cudaFree(t->m); cudaFree(t->v); cudaFree(t->grad); cudaFree(t->w_pi); cudaFree(t->w_vf);
+    cudaFree(t->partial); cudaFree(t->stats); cudaFree(t->mb);
+    delete t;
+    return QS_OK;
+}
+
+int qs_trainer_set_stream(qs_trainer *t, void *stream) { if (!t) return QS_ERR_ARG; t->stream = (cudaStream_t)stream; return QS_OK; }
+
+static int trainer_download(qs_trainer *t) {  // device master parameters -> host mirror
+    QS_TCUDA(t, cudaSetDevice(t->device));
+    if (t->dirty) return QS_OK;  // host copy is the newer one
+    QS_TCUDA(t, cudaMemcpyAsync(t->h_param.data(), t->param, t->h_param.size() * 4, cudaMemcpyDeviceToHost, t->stream));
+    QS_TCUDA(t, cudaStreamSynchronize(t->stream));
+    return QS_OK;
+}
+
+// torch layout in: W (out, in) row-major, b (out).  layer 0..2 hidden, 3 = output (policy: 4 rows, value: 1 row)
+int qs_trainer_set_layer(qs_trainer *t, int net, int layer, const float *W, const float *b) {
+    if (!t) return QS_ERR_ARG;
+    if (net < 0 || net > 1 || layer < 0 || layer > 3 || !W || !b) return tfail(t, QS_ERR_ARG, "qs_trainer_set_layer: bad argument");
+    if (int r = trainer_download(t)) return r;
+    const int n_out = layer == 3 ? (net == 0 ? 4 : 1) : t->hidden, n_in = layer == 0 ? t->in_dim : t->hidden;
+    const int ones = layer == 0 ? t->in_dim : qs::kPolOnes;
+    float *base = t->h_param.data() + (size_t)net * t->nf;
+    for (int o = 0; o < n_out; ++o) {
+        for (int i = 0; i < n_in; ++i) base[tr_index(t, layer, o, i)] = W[(size_t)o * n_in + i];
+        base[tr_index(t, layer, o, ones)] = b[o];
+    }
+    t->dirty = true;
+    return QS_OK;
+}
+
+int qs_trainer_get_layer(qs_trainer *t, int net, int layer, float *W, float *b) {
+    if (!t) return QS_ERR_ARG;
+    if (net < 0 || net > 1 || layer < 0 || layer > 3 || !W || !b) return tfail(t, QS_ERR_ARG, "qs_trainer_get_layer: bad argument");
+    if (int r = trainer_download(t)) return r;
+    const int n_out = layer == 3 ? (net == 0 ? 4 : 1) : t->hidden, n_in = layer == 0 ? t->in_dim : t->hidden;
+    const int ones = layer == 0 ? t->in_dim : qs::kPolOnes;
+    const float *base = t->h_param.data() + (size_t)net * t->nf;
+    for (int o = 0; o < n_out; ++o) {
+        for (int i = 0; i < n_in; ++i) W[(size_t)o * n_in + i] = base[tr_index(t, layer, o, i)];
+        b[o] = base[tr_index(t, layer, o, ones)];
+    }
+    return QS_OK;
+}
+
+int qs_trainer_set_log_std(qs_trainer *t, const float *ls4) {
+    if (!t || !ls4) return QS_ERR_ARG;
+    if (int r = trainer_download(t)) return r;
+    for (int k = 0; k < 4; ++k) t->h_param[2 * (size_t)t->nf + k] = ls4[k];
+    t->dirty = true;
+    return QS_OK;
+}
+int qs_trainer_get_log_std(qs_trainer *t, float *ls4) {
+    if (!t || !ls4) return QS_ERR_ARG;
+    if (int r = trainer_download(t)) return r;
+    for (int k = 0; k < 4; ++k) ls4[k] = t->h_param[2 * (size_t)t->nf + k];
+    return QS_OK;
+}
+
+int qs_trainer_reset_optimizer(qs_trainer *t) {
+    if (!t) return QS_ERR_ARG;
+    QS_TCUDA(t, cudaSetDevice(t->device));
+    const size_t np = 2 * (size_t)t->nf + 4;
+    QS_TCUDA(t, cudaMemsetAsync(t->m, 0, np * 4, t->stream));
+    QS_TCUDA(t, cudaMemsetAsync(t->v, 0, np * 4, t->stream));
+    t->step = 0;
+    return QS_OK;
+}
+
+static void pack_blob_from_params(const qs_trainer *t, int net, std::vector<unsigned char> &blob) {
+    blob.assign(qs::policy_weight_bytes(t->k1, 3), 0);
+    const float *base = t->h_param.data() + (size_t)net * t->nf;
+    size_t off = 0;
+    for (int l = 0; l < 4; ++l) {
+        const int rows = l == 3 ? qs::kPolOut : qs::kPolHidden, kk = l == 0 ? t->k1 : qs::kPolHidden;
+        for (int n = 0; n < rows; ++n)
+            for (int k = 0; k < kk; ++k) {
+                const uint16_t h = bf16_rne(base[tr_index(t, l, n, k)]);
+                memcpy(&blob[off + (size_t)(k / 8) * rows * 16 + (size_t)n * 16 + (size_t)(k % 8) * 2], &h, 2);
+            }
+        off += (size_t)(kk / 8) * rows * 16;
+    }
+}
+
+static int trainer_upload(qs_trainer *t) {
+    if (!t->dirty) return QS_OK;
+    QS_TCUDA(t, cudaStreamSynchronize(t->stream));
+    QS_TCUDA(t, cudaMemcpy(t->param, t->h_param.data(), t->h_param.size() * 4, cudaMemcpyHostToDevice));
+    std::vector<unsigned char> blob;
+    for (int net = 0; net < 2; ++net) {
+        pack_blob_from_params(t, net, blob);
+        QS_TCUDA(t, cudaMemcpy(net == 0 ? t->w_pi : t->w_vf, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    }
+    t->dirty = false;
+    return QS_OK;
+}
+
+// One minibatch: statistics -> gradients of both networks -> reduce -> (apply != 0) clip + Adam + new BF16 weights.
+// All pointers are device pointers into the flat (total, .) rollout buffers; idx_dev (rows) int64 or NULL.
+int qs_trainer_minibatch(qs_trainer *t, const int64_t *idx_dev, int64_t rows, const float *obs, const float *act,
+                         const float *old_logp, const float *adv, const float *ret, const float *weight,
+                         const qs_train_hyper *h, int apply) {
+    if (!t) return QS_ERR_ARG;
+    if (rows <= 0 || !obs || !act || !old_logp || !adv || !ret || !h) return tfail(t, QS_ERR_ARG, "qs_trainer_minibatch: bad argument");
+    if ((uintptr_t)act & 15) return tfail(t, QS_ERR_ARG, "qs_trainer_minibatch: act must be 16-byte aligned");
+    QS_TCUDA(t, cudaSetDevice(t->device));
+    if (int r = trainer_upload(t)) return r;
+    QS_TCUDA(t, cudaMemsetAsync(t->mb, 0, 32, t->stream));
+    qs::ppo_mbstats_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, t->stream>>>((const long long *)idx_dev, rows, adv, weight, t->mb);
+    qs::TrainParams P{};
+    P.idx = (const long long *)idx_dev; P.rows = rows; P.obs = obs; P.act = act; P.old_logp = old_logp; P.adv = adv; P.ret = ret;
+    P.weight = weight; P.mb = t->mb; P.w_pi = t->w_pi; P.w_vf = t->w_vf; P.log_std = t->param + 2 * (size_t)t->nf;
+    P.partial = t->partial; P.in_dim = t->in_dim; P.k1 = t->k1; P.normalize_adv = h->normalize_advantage;
+    P.clip_range = h->clip_range; P.vf_coef = h->vf_coef; P.obs_limit = h->obs_limit; P.act_limit = h->act_limit;
+    P.weight_bytes = qs::policy_weight_bytes(t->k1, 3);
+    const long long tiles = (rows + qs::kPolRows - 1) / qs::kPolRows;
+    int ctas = (int)(2 * tiles < t->n_ctas ? 2 * tiles : t->n_ctas);
+    qs::ppo_grad_kernel<<<ctas, qs::kPolRows, t->smem, t->stream>>>(P);
+    qs::AdamParams A{};
+    A.partial = t->partial; A.n_ctas = ctas; A.k1 = t->k1; A.mb = t->mb; A.grad = t->grad; A.norm2 = t->mb + 3;
+    A.stats_out = t->stats; A.param = t->param; A.m = t->m; A.v = t->v; A.w_pi = t->w_pi; A.w_vf = t->w_vf;
+    A.lr = h->learning_rate; A.beta1 = h->beta1; A.beta2 = h->beta2; A.eps = h->eps; A.max_grad_norm = h->max_grad_norm;
+    A.ent_coef = h->ent_coef;
+    const int total = 2 * t->nf + 8;
+    qs::ppo_reduce_kernel<<<(total + 255) / 256, 256, 0, t->stream>>>(A);
+    t->launches += 3;
+    if (apply) {
+        t->step++;
+        A.bc1 = (float)(1.0 - pow((double)h->beta1, (double)t->step));
+        A.bc2 = (float)(1.0 - pow((double)h->beta2, (double)t->step));
+        qs::ppo_adam_kernel<<<(2 * t->nf + 4 + 255) / 256, 256, 0, t->stream>>>(A);
+        t->launches++;
+    }
+    QS_TCUDA(t, cudaGetLastError());
+    return QS_OK;
+}
+
+// gradients of the last minibatch in torch layout (tests): W (out, in), b (out)
+int qs_trainer_get_grad(qs_trainer *t, int net, int layer, float *W, float *b, float *log_std4) {
+    if (!t) return QS_ERR_ARG;
+    QS_TCUDA(t, cudaSetDevice(t->device));
+    std::vector<float> g(2 * (size_t)t->nf + 4);
+    QS_TCUDA(t, cudaMemcpyAsync(g.data(), t->grad, g.size() * 4, cudaMemcpyDeviceToHost, t->stream));
+    QS_TCUDA(t, cudaStreamSynchronize(t->stream));
+    if (log_std4) for (int k = 0; k < 4; ++k) log_std4[k] = g[2 * (size_t)t->nf + k];
+    if (W && b) {
+        if (net < 0 || net > 1 || layer < 0 || layer > 3) return tfail(t, QS_ERR_ARG, "qs_trainer_get_grad: bad argument");
+        const int n_out = layer == 3 ? (net == 0 ? 4 : 1) : t->hidden, n_in = layer == 0 ? t->in_dim : t->hidden;
+        const int ones = layer == 0 ? t->in_dim : qs::kPolOnes;
+        const float *base = g.data() + (size_t)net * t->nf;
+        for (int o = 0; o < n_out; ++o) {
+            for (int i = 0; i < n_in; ++i) W[(size_t)o * n_in + i] = base[tr_index(t, layer, o, i)];
+            b[o] = base[tr_index(t, layer, o, ones)];
+        }
+    }
+    return QS_OK;
+}
+
+// accumulated loss statistics since the last reset: pg_loss, v_loss, clip_frac, approx_kl (sums of minibatch means),
+// grad_norm (sum), 3 unused
+int qs_trainer_get_stats(qs_trainer *t, float *out8, int reset) {
+    if (!t || !out8) return QS_ERR_ARG;
+    QS_TCUDA(t, cudaSetDevice(t->device));
+    QS_TCUDA(t, cudaMemcpyAsync(out8, t->stats, 32, cudaMemcpyDeviceToHost, t->stream));
+    if (reset) QS_TCUDA(t, cudaMemsetAsync(t->stats, 0, 32, t->stream));
+    QS_TCUDA(t, cudaStreamSynchronize(t->stream));
+    return QS_OK;
+}
+
+// publish the policy network to the device actor without a host round trip: same BF16 blob layout
+int qs_trainer_publish(qs_trainer *t, qs_policy *p) {
+    if (!t || !p) return QS_ERR_ARG;
+    if (p->in_dim != t->in_dim || p->n_hidden != 3 || p->hidden != t->hidden || p->out_dim != 4 || p->device != t->device)
+        return tfail(t, QS_ERR_ARG, "qs_trainer_publish: policy shape differs from the trainer's");
+    if (int r = trainer_upload(t)) return r;
+    QS_TCUDA(t, cudaMemcpyAsync(p->w_dev, t->w_pi, qs::policy_weight_bytes(t->k1, 3), cudaMemcpyDeviceToDevice, t->stream));
+    float ls[4];
+    QS_TCUDA(t, cudaMemcpyAsync(ls, t->param + 2 * (size_t)t->nf, 16, cudaMemcpyDeviceToHost, t->stream));
+    QS_TCUDA(t, cudaStreamSynchronize(t->stream));
+    for (int k = 0; k < 4; ++k) p->std[k] = expf(ls[k]);
+    p->dirty = false;
+    for (int l = 0; l <= p->n_hidden; ++l) p->have[l] = true;
+    return QS_OK;
 }
 
 }  // extern "C"

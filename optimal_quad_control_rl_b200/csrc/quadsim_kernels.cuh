@@ -802,7 +802,11 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
         bool write_world = active, write_dist = false;
         if (P.mode == kModeNormal) {
             if (P.reset_source == kResetDevice) {  // warp-uniform branch: the whole warp takes part in the draw
+#ifdef QS_EXP_NORESET  // experiment only: what the fused reset path costs
+                const bool need = false;
+#else
                 const bool need = dn && active;
+#endif
                 // scratch = the head of this warp's observation slice: its previous bulk store must have been read
                 if (__any_sync(0xffffffffu, need)) {
                     if (lane == 0 && obs_in_flight) bulk_store_wait_read();

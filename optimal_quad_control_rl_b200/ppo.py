@@ -283,7 +283,11 @@ class PPO:
         self.rollout = "device" if (rollout != "host" and can_device) else "host"
         # SB3 always bootstraps from infos; on the device path it is opt-in (the reference's aliased infos make it wrong)
         self.bootstrap = bootstrap if bootstrap is not None else ("sb3_a8" if self.rollout == "host" else "none")
-        self.update = "torch" if update == "auto" else update
+        from .train_fused import fused_supported
+        if update == "fused" and not fused_supported(self.policy):
+            raise ValueError("update='fused' needs ReLU pi / vf networks of three equal hidden layers (<= 127 wide), "
+                             "observations <= 63 wide")
+        self.update = ("fused" if fused_supported(self.policy) else "torch") if update == "auto" else update
         self.actor = None
         if fits:
             self.actor = MlpPolicy(*self._pi_arrays(), std=self.policy.log_std.detach().exp().cpu().numpy(), device=self.device,

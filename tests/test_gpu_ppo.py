@@ -122,7 +122,7 @@ def test_ppo_checkpoint_round_trip_and_controller_export(tmp_path, tracks):
     a1, _ = ppo.predict(obs, deterministic=True)
     a2, _ = again.predict(obs, deterministic=True)
     np.testing.assert_array_equal(a1, a2)
-    again.learn(iterations=1)  # optimizer state restored: training continues
+    again.learn(iterations=1, reset_num_timesteps=False)  # optimizer state restored: training continues (`:820`)
     assert again.num_timesteps == 3 * 16 * 1024
     # ---- C export of the actor
     files = Q.export_controller(ppo, env, str(tmp_path / "c_code"))
@@ -294,8 +294,9 @@ def test_device_rollout_a8_bootstrap_and_host_rollout_agree_on_semantics(tracks)
     assert ((fl & 2) != 0).any() and (((fl & 1) != 0) == dn).all()
     # recompute from the raw pieces: the device rewards minus the bootstrap must be what the env returned
     obs_next = b["obs"][1:].cpu().numpy()
-    with torch.no_grad():
-        V = lambda o: ppo._values(torch.as_tensor(o, device=ppo.device)).cpu().numpy()
+    def V(o):
+        with torch.no_grad():
+            return ppo._values(torch.as_tensor(o, device=ppo.device)).cpu().numpy()
     add = np.zeros_like(fl, dtype=np.float32)
     for t in range(48):                                   # SB3's loop over the reference's aliased infos
         info = {}
@@ -313,6 +314,8 @@ def test_device_rollout_a8_bootstrap_and_host_rollout_agree_on_semantics(tracks)
                   bootstrap="none")
     b2 = plain.collect_rollouts()
     assert torch.equal(b2["dones"], b["dones"]) and torch.equal(b2["obs"], b["obs"])
-    np.testing.assert_allclose(b["rewards"].cpu().numpy(), b2["rewards"].cpu().numpy() + add, rtol=1e-5, atol=1e-5)
+    # (the values are TF32 GEMMs whose last bits depend on the batch shape: (T, D) there, (1, D) here)
+    np.testing.assert_allclose(b["rewards"].cpu().numpy(), b2["rewards"].cpu().numpy() + add, rtol=1e-2, atol=2e-3)
+    assert np.array_equal(b["rewards"].cpu().numpy() != b2["rewards"].cpu().numpy(), add != 0)
     assert np.abs(add).sum() > 0
     env.close(); env2.close()
