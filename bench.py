@@ -557,7 +557,7 @@ def run_ours(a):
     if a.workload != "step":
         if a.variant != "e2e" or ga != 1:
             raise SystemExit("--workload policy/rollout uses the shipped 24-input controller: e2e, --gates-ahead 1")
-        pol = Q.MlpPolicy.from_npz(device=dev, seed=3, env_offset=rank * n)
+        pol = Q.MlpPolicy.reference_controller(device=dev, seed=3, env_offset=rank * n)
         obs_in = [torch.randn((n, env.state_len), generator=gen, device=dev) for _ in range(4)]
 
     def one_step(i):

@@ -362,7 +362,7 @@ __global__ void ppo_mbstats_kernel(const long long *idx, long long rows, const f
     if (r < rows) {
         const long long s = idx ? idx[r] : r;
         w = weight ? (double)weight[s] : 1.0;
-        a = (double)adv[s];
+        a = w != 0.0 ? (double)adv[s] : 0.0;  // a masked sample may carry anything
     }
     double v0 = w, v1 = w * a, v2 = w * a * a;
 #pragma unroll

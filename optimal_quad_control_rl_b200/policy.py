@@ -56,10 +56,19 @@ class MlpPolicy:
 
     @classmethod
     def from_npz(cls, path=None, **kw):
-        """Default: the reference's shipped controller (24 -> 120 -> 120 -> 120 -> 4, `c_code/neural_network.c`)."""
-        z = np.load(path or os.path.join(_DATA, "policy_k4.npz"))
+        """Default: the controller this repository trained on the E2E zigzag env with its own PPO (130 s on one B200,
+        profiles/r2/ppo; 16-18 gates per 12 s episode without a crash, also when exported to C and flown against the
+        CPU oracle env, tests/test_trained_policy_cpu.py)."""
+        z = np.load(path or os.path.join(_DATA, "policy_e2e_zigzag_ppo.npz"))
         n = len(z["dims"]) - 1
         return cls([z[f"W{l}"] for l in range(n)], [z[f"b{l}"] for l in range(n)], std=z["std"], **kw)
+
+    @classmethod
+    def reference_controller(cls, **kw):
+        """The reference's shipped controller (24 -> 120 -> 120 -> 120 -> 4, `c_code/neural_network.c`, std
+        `c_code/nn_controller.c:7-12`).  It was trained on the rectangle track with another env build and passes hardly
+        any gate here: a fixture for parity with the reference's own C network, not a pilot."""
+        return cls.from_npz(os.path.join(_DATA, "policy_k4.npz"), **kw)
 
     @classmethod
     def from_sb3(cls, model, **kw):

@@ -105,7 +105,7 @@ def test_device_rollout_equals_manual_loop(tracks):
         env = Q.Quadcopter3DGates(n, gp, gy, sp, gates_ahead=1, reset_rng="device", seed=2)
         env.disturbance_ranges = Q.training_disturbance_ranges()
         env.max_steps = 10  # time-limit resets inside the rollout (the trained controller rarely crashes)
-        pol = Q.MlpPolicy.from_npz(seed=8)
+        pol = Q.MlpPolicy.reference_controller(seed=8)
         obs0 = env.reset_tensor().clone()
         if fused:
             r = env.rollout(pol, steps)
@@ -140,7 +140,7 @@ def test_rollout_buffers_are_consistent_with_device_totals(tracks):
     n, steps = 4096, 200
     env = Q.Quadcopter3DGates(n, gp, gy, sp, gates_ahead=1, reset_rng="device", seed=1)
     env.disturbance_ranges = Q.training_disturbance_ranges()
-    pol = Q.MlpPolicy.from_npz()
+    pol = Q.MlpPolicy.reference_controller()
     env.enable_stats(True)
     obs0 = env.reset_tensor().clone()
     r = env.rollout(pol, steps, deterministic=True)

@@ -1,5 +1,5 @@
-"""Rows f2 -> f3 end to end, on the CPU: the policy PPO trained on the GPU simulator (330 s on one B200,
-profiles/r1/ppo/) is exported to the reference's flight-controller C files, compiled with gcc, and flown closed loop
+"""Rows f2 -> f3 end to end, on the CPU: the policy PPO trained on the GPU simulator (130 s on one B200 with the
+tcgen05 update kernels, profiles/r2/ppo/) is exported to the reference's flight-controller C files, compiled with gcc, and flown closed loop
 against the CPU ORACLE env (the restatement pinned to the reference) -- the reference's own acceptance test
 (`3D quad race.ipynb:4487-4521`: crash rate of the C controller over simulated episodes).  If the GPU simulator's
 dynamics, observation transform or reward differed from the reference's, a policy trained there would not fly here.
@@ -46,4 +46,4 @@ def test_gpu_trained_policy_flies_the_oracle_env_through_generated_c(tmp_path, t
         gates.append(passed); lengths.append(t + 1)
     print("gates per episode", gates, "lengths", lengths, "crashes", crashes)
     assert crashes <= 1                      # the reference reports the crash rate of its C controller the same way
-    assert np.mean(gates) >= 9               # 12.9 per episode in training (with exploration noise)
+    assert np.mean(gates) >= 12              # 15.2 per episode in training (with exploration noise)

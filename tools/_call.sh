@@ -1,2 +1,4 @@
-timeout 600 python -m pytest tests/test_gpu_train.py -q -s 2>&1 | tail -80
-timeout 600 python -m pytest tests/test_gpu_ppo.py -q 2>&1 | tail -15
+bash tools/gpu.sh check c4
+bash tools/gpu.sh ppo c4f 130
+bash tools/gpu.sh ppo c4t 45 --update torch --amp
+bash tools/gpu.sh ncu-train c4

@@ -4,7 +4,8 @@
 #   check              pytest -m gpu + smoke()
 #   bench              the bench lines: default (E2E 2^20 + configs), INDI, the reference arm, policy / rollout workloads
 #   ncu                launch list of a short bench + `ncu --set full` of the E2E and INDI step kernels (+ steady-state DRAM traffic)
-#   ncu-tc             `ncu --set full` of the tcgen05 kernels (policy, fused rollout, PPO training kernel)
+#   ncu-tc             `ncu --set full` of the tcgen05 kernels (policy, fused rollout)
+#   ncu-train          `ncu --set full` of the PPO training kernel + launch list of one update
 #   variants [libs..]  bench.py over experimental builds / launch modes of the step kernel (QS_LIB, QS_* env switches)
 #   nsweep  [libs..]   per-step time vs N (2^16 .. 2^22) for the product library and each extra library
 #   numpy              the NumPy-facing env.step (what SB3 calls) at N = 100 .. 2^20
@@ -28,7 +29,14 @@ if 'cpu_baseline' in d: print('    cpu', d['cpu_baseline']['kind'], '%.4g' % d['
 }
 Q="--no-cpu-baseline --no-configs --e2e-steps 3"
 case $cmd in
-build-variants)
+build-ncu-train)
+  ncu --set full --import-source on --clock-control none -k regex:ppo_grad_kernel -s 30 -c 1 -o gpurun_out/${tag}_ppo_grad -f \
+      python tools/train_ppo.py --num-envs 65536 --iterations 2 --update fused > gpurun_out/${tag}_ncu_train.log 2>&1
+  ncu --metrics gpu__time_duration.sum --clock-control none -k regex:ppo_ -s 200 -c 40 --csv --log-file gpurun_out/${tag}_train_launches.csv \
+      python tools/train_ppo.py --num-envs 65536 --iterations 2 --update fused > /dev/null 2>&1
+  ls -la gpurun_out/${tag}_*.ncu-rep
+  ;;
+variants)
   mkdir -p build/exp
   python - "$tag" "$@" <<'PY'
 import sys; sys.path.insert(0, '.')
@@ -68,6 +76,13 @@ ncu-tc)
       python bench.py --workload policy --steps 8 --warmup 20 --graph 0 > gpurun_out/${tag}_ncu_policy.log 2>&1
   ncu --set full --import-source on --clock-control none -k regex:rollout_kernel -s 2 -c 1 -o gpurun_out/${tag}_rollout_fused -f \
       python bench.py --workload rollout_fused --rollout-steps 8 --steps 16 --warmup 16 > gpurun_out/${tag}_ncu_rollout.log 2>&1
+  ls -la gpurun_out/${tag}_*.ncu-rep
+  ;;
+ncu-train)
+  ncu --set full --import-source on --clock-control none -k regex:ppo_grad_kernel -s 30 -c 1 -o gpurun_out/${tag}_ppo_grad -f \
+      python tools/train_ppo.py --num-envs 65536 --iterations 2 --update fused > gpurun_out/${tag}_ncu_train.log 2>&1
+  ncu --metrics gpu__time_duration.sum --clock-control none -k regex:ppo_ -s 200 -c 40 --csv --log-file gpurun_out/${tag}_train_launches.csv \
+      python tools/train_ppo.py --num-envs 65536 --iterations 2 --update fused > /dev/null 2>&1
   ls -la gpurun_out/${tag}_*.ncu-rep
   ;;
 variants)
