@@ -244,18 +244,27 @@ class ClockSampler(threading.Thread):
 
 
 def nvlink_kib(index):
-    """(tx, rx) data KiB moved over all NVLinks of GPU `index` so far (NVML throughput counters), or None."""
+    """(tx, rx) data KiB moved over all NVLinks of GPU `index` so far, or None: NVML's throughput field values (scope =
+    all links), else the per-link counters `nvidia-smi nvlink -gt d` prints, summed."""
     try:
         import pynvml as nv
         nv.nvmlInit()
         h = nv.nvmlDeviceGetHandleByIndex(index)
-        vals = nv.nvmlDeviceGetFieldValues(h, [nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX])
-        out = []
-        for v in vals:
-            if v.nvmlReturn != 0:
-                return None
-            out.append(int(v.value.ullVal))
-        return tuple(out)
+        all_links = 0xFFFFFFFF  # scopeId UINT_MAX = sum over the links (scopeId 0 would be link 0 only)
+        vals = nv.nvmlDeviceGetFieldValues(h, [(nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, all_links),
+                                               (nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, all_links)])
+        if any(v.nvmlReturn != 0 for v in vals):
+            raise RuntimeError("field value unavailable")
+        return tuple(int(v.value.ullVal) for v in vals)
+    except Exception:
+        pass
+    try:
+        import re
+        import subprocess
+        txt = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True, timeout=10).stdout
+        tx = sum(int(x) for x in re.findall(r"Data Tx:\s*(\d+)\s*KiB", txt))
+        rx = sum(int(x) for x in re.findall(r"Data Rx:\s*(\d+)\s*KiB", txt))
+        return (tx, rx) if re.search(r"Data Tx", txt) else None
     except Exception:
         return None
 

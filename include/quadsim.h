@@ -196,6 +196,10 @@ int qs_get_state_layout(qs_env *env, void **base, int *block_bytes, int *offsets
 typedef struct qs_policy qs_policy; /* opaque */
 int qs_policy_create(qs_policy **out, int in_dim, int n_hidden, int hidden_dim, int out_dim, int device, void *stream);
 int qs_policy_destroy(qs_policy *policy);
+/* hidden activation: SB3's `activation_fn` (`3D quad race.ipynb:784`: torch.nn.ReLU; SB3's default is Tanh); the
+ * reference's generated C has both (`nn_relu` / `nn_tanh`, c_code/neural_network.c:407-417).  tanh needs hidden_dim <= 120. */
+typedef enum { QS_ACT_RELU = 0, QS_ACT_TANH = 1 } qs_activation;
+int qs_policy_set_activation(qs_policy *policy, int activation);
 const char *qs_policy_last_error(const qs_policy *policy); /* NULL: error of the last failed qs_policy_create */
 int qs_policy_set_stream(qs_policy *policy, void *stream);
 /* layer 0..n_hidden (the last is the output layer); W row-major [out][in] and b [out] as torch / the generated C

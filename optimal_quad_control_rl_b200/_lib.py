@@ -81,6 +81,7 @@ SIGNATURES = {
     "qs_policy_set_stream": (C.c_int, [_vp, _vp]),
     "qs_policy_set_layer": (C.c_int, [_vp, C.c_int, _fp, _fp]),
     "qs_policy_set_std": (C.c_int, [_vp, _fp]),
+    "qs_policy_set_activation": (C.c_int, [_vp, C.c_int]),
     "qs_policy_seed": (C.c_int, [_vp, C.c_uint64]),
     "qs_policy_set_env_offset": (C.c_int, [_vp, C.c_int64]),
     "qs_policy_forward": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int]),

@@ -44,6 +44,8 @@ struct qs_env {
     // staging for the host-buffer entry points
     float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr;
     float *act_stage = nullptr;  // pinned host staging for pageable / float64 actions (qs_step_host_ex)
+    unsigned long long *info_dev = nullptr, *info_host = nullptr;  // step_info_kernel result (3 words) + its pinned copy
+    cudaEvent_t ev_info = nullptr;
     uint8_t *h_done = nullptr, *h_flags = nullptr;
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -258,6 +260,9 @@ int qs_destroy(qs_env *e) {
     cudaFree(s.base); cudaFree(e->epoch_dev); cudaFree(e->track_dev); cudaFree(e->stats_dev); cudaFree(e->scratch);
     cudaFree(e->h_act); cudaFree(e->h_obs); cudaFree(e->h_rew); cudaFree(e->h_done); cudaFree(e->h_flags);
     if (e->act_stage) cudaFreeHost(e->act_stage);
+    cudaFree(e->info_dev);
+    if (e->info_host) cudaFreeHost(e->info_host);
+    if (e->ev_info) cudaEventDestroy(e->ev_info);
     if (e->copy_a) cudaStreamDestroy(e->copy_a);
     if (e->copy_b) cudaStreamDestroy(e->copy_b);
     if (e->ev_in) cudaEventDestroy(e->ev_in);
@@ -601,10 +606,12 @@ int qs_step_host_ex(qs_env *e, const void *act, int act_dtype, float *obs, float
     P.obs = e->h_obs; P.rew = e->h_rew; P.done = e->h_done; P.flags = flags ? e->h_flags : nullptr;
     P.mode = mode; P.reset_source = reset_source;
     const long long tiles = (e->n + qs::kBlock - 1) / qs::kBlock;
-    long long per = (tiles + e->host_chunks - 1) / e->host_chunks;
+    const bool stage = act_dtype == QS_F64 || !is_pinned_host(act);
+    // staging the actions on the host puts the first chunk's memcpy on the critical path: twice as many chunks then
+    const int chunks = stage ? 2 * e->host_chunks : e->host_chunks;
+    long long per = (tiles + chunks - 1) / chunks;
     if (per < 256) per = tiles < 256 ? tiles : 256;  // >= 32768 envs per chunk: below that the copies are latency-bound
     const bool want_obs = obs && mode != QS_MODE_PAUSE;
-    const bool stage = act_dtype == QS_F64 || !is_pinned_host(act);
     if (stage && !e->act_stage) QS_CUDA(e, cudaHostAlloc((void **)&e->act_stage, (size_t)e->n * 16, cudaHostAllocDefault));
     QS_CUDA(e, cudaEventRecord(e->ev_in, e->stream));
     QS_CUDA(e, cudaStreamWaitEvent(e->copy_a, e->ev_in, 0));
@@ -635,21 +642,28 @@ int qs_step_host_ex(qs_env *e, const void *act, int act_dtype, float *obs, float
         QS_CUDA(e, cudaMemcpyAsync(done + first, e->h_done + first, cnt, cudaMemcpyDeviceToHost, e->copy_b));
         if (flags) QS_CUDA(e, cudaMemcpyAsync(flags + first, e->h_flags + first, cnt, cudaMemcpyDeviceToHost, e->copy_b));
     }
+    if (info) {  // the `infos` scan (`:589-594`) as one tiny kernel over the flag bytes, behind the last chunk's step
+        if (!e->info_dev) {
+            QS_CUDA(e, cudaMalloc(&e->info_dev, 24));
+            QS_CUDA(e, cudaHostAlloc((void **)&e->info_host, 24, cudaHostAllocDefault));
+            QS_CUDA(e, cudaEventCreateWithFlags(&e->ev_info, cudaEventDisableTiming));
+        }
+        QS_CUDA(e, cudaMemsetAsync(e->info_dev, 0, 24, e->copy_a));
+        qs::step_info_kernel<<<148, 256, 0, e->copy_a>>>(e->h_flags, e->n, e->info_dev);
+        e->launches++;
+        QS_CUDA(e, cudaMemcpyAsync(e->info_host, e->info_dev, 24, cudaMemcpyDeviceToHost, e->copy_a));
+        QS_CUDA(e, cudaEventRecord(e->ev_info, e->copy_a));
+        QS_CUDA(e, cudaStreamWaitEvent(e->copy_b, e->ev_info, 0));
+    }
     QS_CUDA(e, cudaGetLastError());
     QS_CUDA(e, cudaEventRecord(e->ev_out, e->copy_b));
     QS_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_out, 0));  // later work on the handle's stream is ordered after us
     QS_CUDA(e, cudaEventSynchronize(e->ev_out));
-    if (info) {  // one pass over the flag bytes that just arrived (1 B/env): nothing for the caller to scan
-        int64_t last = -1, nd = 0;
-        uint8_t any = 0;
-        const uint8_t *f = flags;
-        for (int64_t i = 0; i < e->n; ++i) {
-            any |= f[i];
-            if (f[i] & QS_F_DONE) { last = i; ++nd; }
-        }
-        info->last_done_index = (mode == QS_MODE_PAUSE) ? -1 : last;
-        info->n_done = (mode == QS_MODE_PAUSE) ? 0 : nd;
-        info->any_truncated = (any & QS_F_TRUNCATED) ? 1 : 0;
+    if (info) {
+        const bool paused = mode == QS_MODE_PAUSE;  // env.pause clears the dones (`:570-572`), not the time-limit test
+        info->last_done_index = paused ? -1 : (int64_t)e->info_host[0] - 1;
+        info->n_done = paused ? 0 : (int64_t)e->info_host[1];
+        info->any_truncated = e->info_host[2] ? 1 : 0;
     }
     return QS_OK;
 }
@@ -687,6 +701,7 @@ struct qs_policy {
     unsigned char *w_dev = nullptr;
     unsigned long long *epoch_dev = nullptr;
     bool dirty = true, pdl = true;
+    int activation = 0;  // 0 ReLU, 1 tanh
     uint64_t seed = 0, launches = 0;
     int64_t env_offset = 0;
     float std[4] = {0, 0, 0, 0};
@@ -806,6 +821,17 @@ int qs_policy_set_layer(qs_policy *p, int layer, const float *W, const float *b)
     return QS_OK;
 }
 
+// hidden activation (SB3 `activation_fn`; the reference's generated C carries both `nn_relu` and `nn_tanh`).  With tanh the
+// bias-carrying constant unit cannot be re-emitted through the activation (tanh(1) != 1): it has to sit in the slab the
+// kernels never overwrite, i.e. hidden_dim <= 120.
+int qs_policy_set_activation(qs_policy *p, int activation) {
+    QS_PCHECK(p);
+    if (activation != QS_ACT_RELU && activation != QS_ACT_TANH) return pfail(p, QS_ERR_ARG, "qs_policy_set_activation: 0 = relu, 1 = tanh");
+    if (activation == QS_ACT_TANH && p->hidden > qs::kPolHidden - 8) return pfail(p, QS_ERR_ARG, "qs_policy_set_activation: tanh needs hidden_dim <= 120");
+    p->activation = activation;
+    return QS_OK;
+}
+
 int qs_policy_set_std(qs_policy *p, const float *std4) {
     QS_PCHECK(p);
     if (!std4) return pfail(p, QS_ERR_ARG, "qs_policy_set_std: NULL");
@@ -827,7 +853,7 @@ static int policy_params(qs_policy *p, int64_t n, int deterministic, cudaStream_
     }
     P.weights = p->w_dev; P.epoch = p->epoch_dev;
     P.n = n; P.env_offset = p->env_offset; P.seed = p->seed; P.in_dim = p->in_dim; P.k1 = p->k1; P.n_hidden = p->n_hidden; P.hidden = p->hidden;
-    P.out_dim = p->out_dim; P.deterministic = deterministic;
+    P.out_dim = p->out_dim; P.deterministic = deterministic; P.activation = p->activation;
     P.weight_bytes = qs::policy_weight_bytes(p->k1, p->n_hidden);
     P.tmem_cols = p->groups <= 1 ? 128u : (p->groups == 2 ? 256u : 512u);
     for (int k = 0; k < 4; ++k) P.std[k] = p->std[k];

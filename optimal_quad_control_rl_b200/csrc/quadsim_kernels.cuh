@@ -1019,6 +1019,30 @@ __global__ void __launch_bounds__(kBlock) apply_reset_kernel(const __grid_consta
     for (int j = 0; j < P.obs_len; ++j) dst[j] = row[j];
 }
 
+// What step_wait's per-env `infos` loop computes (`3D quad race.ipynb:589-594`), from the flag bytes of a step: the highest
+// done env index (its observation row becomes the ONE aliased dict's "terminal_observation"), the number of done envs
+// and whether any env was truncated.  out: [0] last done index + 1 (0 = none), [1] done count, [2] any-truncated.
+__global__ void step_info_kernel(const uint8_t *flags, long long n, unsigned long long *out) {
+    unsigned long long last1 = 0, cnt = 0, tr = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const uint32_t f = flags[i];
+        if (f & F_DONE) { last1 = (unsigned long long)i + 1ull; ++cnt; }
+        tr |= (f & F_TRUNC) ? 1ull : 0ull;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, last1, o);
+        last1 = a > last1 ? a : last1;
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        tr |= __shfl_xor_sync(0xffffffffu, tr, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (last1) atomicMax(out, last1);
+        if (cnt) atomicAdd(out + 1, cnt);
+        if (tr) atomicOr(out + 2, 1ull);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ AoS <-> planes
 template <int V>
 __global__ void import_kernel(Planes s, long long first, long long count, const float *ws, const float *dist,

@@ -47,6 +47,7 @@ struct PolicyParams {
     int hidden;               // real hidden width (<= 127); units hidden..126 are zero padding, unit 127 the constant 1
     int out_dim;              // <= 4
     int deterministic;
+    int activation;           // hidden activation: 0 = ReLU (`nn_relu`), 1 = tanh (`nn_tanh`, c_code/neural_network.c:413-417)
     uint32_t weight_bytes;
     uint32_t tmem_cols;       // accumulator columns to allocate: 128 per tile group, rounded up to a power of two
     float std[4];
@@ -151,19 +152,42 @@ __device__ __forceinline__ void relu_pack_store(const uint32_t *v, unsigned char
         *reinterpret_cast<uint4 *>(slab0_row + q * kSlab) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
+// tanh hidden activation (SB3's default `activation_fn`; the reference's generated C has `nn_tanh` next to `nn_relu`):
+// MUFU.TANH (max rel. error ~2^-11, below the BF16 rounding that follows)
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+template <int kSlabs>
+__device__ __forceinline__ void tanh_pack_store(const uint32_t *v, unsigned char *slab0_row) {
+#pragma unroll
+    for (int q = 0; q < kSlabs; ++q) {
+        uint32_t w[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+            w[h] = pack_bf16(tanh_fast(__uint_as_float(v[q * 8 + 2 * h])), tanh_fast(__uint_as_float(v[q * 8 + 2 * h + 1])));
+        *reinterpret_cast<uint4 *>(slab0_row + q * kSlab) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+template <int kSlabs>
+__device__ __forceinline__ void act_pack_store(const uint32_t *v, unsigned char *slab0_row, int act) {
+    if (act == 0) relu_pack_store<kSlabs>(v, slab0_row);
+    else tanh_pack_store<kSlabs>(v, slab0_row);
+}
 // Columns 96..127 of a hidden layer.  With hidden <= 120 the last slab (units 120..126 = zero padding, unit 127 = the
 // constant 1 of the bias folding) never changes: it is written once per kernel (init_const_slab) and neither read
 // from TMEM nor stored again -- 6 % less of the TMEM read-out that bounds this kernel.
-__device__ __forceinline__ void epilogue_tail(uint32_t t_lane, unsigned char *s_a_row, bool const_last, uint32_t *v) {
+__device__ __forceinline__ void epilogue_tail(uint32_t t_lane, unsigned char *s_a_row, bool const_last, uint32_t *v, int act) {
     if (const_last) {
         tmem_ld16(t_lane + 96u, v);
         tmem_ld8p(t_lane + 112u, v + 16);
         tmem_ld_wait();
-        relu_pack_store<3>(v, s_a_row + 12 * kSlab);
+        act_pack_store<3>(v, s_a_row + 12 * kSlab, act);
     } else {
         tmem_ld32(t_lane + 96u, *reinterpret_cast<uint32_t (*)[32]>(v));
         tmem_ld_wait();
-        relu_pack_store<4>(v, s_a_row + 12 * kSlab);
+        act_pack_store<4>(v, s_a_row + 12 * kSlab, act);
     }
 }
 __device__ __forceinline__ void init_const_slab(unsigned char *s_a_row) {  // {0 x 7, 1.0} in BF16
@@ -300,15 +324,15 @@ __global__ void __launch_bounds__(4 * kPolRows, 1) policy_kernel(const __grid_co
                     tmem_ld32(t_lane, v0);
                     tmem_ld32(t_lane + 32u, v1);
                     tmem_ld_wait();
-                    relu_pack_store<4>(v0, s_a + tid * 16);
-                    relu_pack_store<4>(v1, s_a + 4 * kSlab + tid * 16);
+                    act_pack_store<4>(v0, s_a + tid * 16, P.activation);
+                    act_pack_store<4>(v1, s_a + 4 * kSlab + tid * 16, P.activation);
                     tmem_ld32(t_lane + 64u, v0);
                     if (const_last) { tmem_ld16(t_lane + 96u, v1); tmem_ld8p(t_lane + 112u, v1 + 16); }
                     else tmem_ld32(t_lane + 96u, v1);
                     tmem_ld_wait();
-                    relu_pack_store<4>(v0, s_a + 8 * kSlab + tid * 16);
-                    if (const_last) relu_pack_store<3>(v1, s_a + 12 * kSlab + tid * 16);
-                    else relu_pack_store<4>(v1, s_a + 12 * kSlab + tid * 16);
+                    act_pack_store<4>(v0, s_a + 8 * kSlab + tid * 16, P.activation);
+                    if (const_last) act_pack_store<3>(v1, s_a + 12 * kSlab + tid * 16, P.activation);
+                    else act_pack_store<4>(v1, s_a + 12 * kSlab + tid * 16, P.activation);
                 }
             } else {
                 uint32_t v[8];

@@ -188,9 +188,9 @@ __global__ void __launch_bounds__(4 * kPolRows, 1) rollout_kernel(const __grid_c
                     for (int c = 0; c < 3; ++c) {
                         tmem_ld32(t_lane + (uint32_t)c * 32u, v0);
                         tmem_ld_wait();
-                        relu_pack_store<4>(v0, s_a + (c * 4) * kSlab + tid * 16);
+                        act_pack_store<4>(v0, s_a + (c * 4) * kSlab + tid * 16, Q.activation);
                     }
-                    epilogue_tail(t_lane, s_a + tid * 16, const_last, v0);
+                    epilogue_tail(t_lane, s_a + tid * 16, const_last, v0, Q.activation);
                 } else {
                     uint32_t v[8];
                     tmem_ld8(t_lane, v);

@@ -20,7 +20,7 @@ class MlpPolicy:
     """``weights[l]`` is ``(out, in)`` float32 (torch / generated-C layout), ``biases[l]`` is ``(out,)``; the last
     pair is the output layer.  ``std`` = exp(log_std) of the Gaussian action distribution."""
 
-    def __init__(self, weights, biases, std=None, device=None, seed=0, env_offset=0):
+    def __init__(self, weights, biases, std=None, device=None, seed=0, env_offset=0, activation="relu"):
         if not torch.cuda.is_available():
             raise L.QuadsimError("no CUDA device: the policy only runs on the GPU (there is no CPU fallback)")
         self._lib = L.load()
@@ -51,6 +51,10 @@ class MlpPolicy:
         for l, (w, b) in enumerate(zip(self.weights, self.biases)):
             self._call("qs_policy_set_layer", l, w.ctypes.data_as(L._fp), b.ctypes.data_as(L._fp))
         self._call("qs_policy_set_std", self.std.ctypes.data_as(L._fp))
+        if activation not in ("relu", "tanh"):
+            raise ValueError("activation must be 'relu' or 'tanh'")
+        self.activation = activation
+        self._call("qs_policy_set_activation", 1 if activation == "tanh" else 0)
         self._call("qs_policy_seed", int(seed))
         self._call("qs_policy_set_env_offset", int(env_offset))
 
@@ -77,6 +81,9 @@ class MlpPolicy:
         lin = [m for m in pol.mlp_extractor.policy_net if hasattr(m, "weight")] + [pol.action_net]
         w = [m.weight.detach().cpu().numpy() for m in lin]
         b = [m.bias.detach().cpu().numpy() for m in lin]
+        act = getattr(pol, "activation_fn", None)
+        if act is not None and "activation" not in kw:
+            kw["activation"] = "tanh" if getattr(act, "__name__", "") == "Tanh" else "relu"
         return cls(w, b, std=pol.log_std.detach().exp().cpu().numpy(), **kw)
 
     def _call(self, name, *args):

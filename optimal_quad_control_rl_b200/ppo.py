@@ -274,12 +274,12 @@ class PPO:
         # ---- which collector / bootstrap / update
         from .envs import _QuadGatesBase
         pi, vf = self.policy.net_arch["pi"], self.policy.net_arch["vf"]
-        relu = self.policy.activation_fn is nn.ReLU
-        fits = relu and 1 <= len(pi) <= 4 and len(set(pi)) == 1 and pi[0] <= 127
+        act = {nn.ReLU: "relu", nn.Tanh: "tanh"}.get(self.policy.activation_fn)
+        fits = act is not None and 1 <= len(pi) <= 4 and len(set(pi)) == 1 and pi[0] <= (127 if act == "relu" else 120)
         can_device = isinstance(self.venv, _QuadGatesBase) and getattr(self.venv, "reset_rng", "") == "device" and fits
         if rollout == "device" and not can_device:
-            raise ValueError("rollout='device' needs the GPU env with reset_rng='device' and a ReLU policy of 1-4 equal "
-                             "hidden layers <= 127 wide")
+            raise ValueError("rollout='device' needs the GPU env with reset_rng='device' and a ReLU / Tanh policy of 1-4 "
+                             "equal hidden layers <= 127 (ReLU) / 120 (Tanh) wide")
         self.rollout = "device" if (rollout != "host" and can_device) else "host"
         # SB3 always bootstraps from infos; on the device path it is opt-in (the reference's aliased infos make it wrong)
         self.bootstrap = bootstrap if bootstrap is not None else ("sb3_a8" if self.rollout == "host" else "none")
@@ -291,7 +291,7 @@ class PPO:
         self.actor = None
         if fits:
             self.actor = MlpPolicy(*self._pi_arrays(), std=self.policy.log_std.detach().exp().cpu().numpy(), device=self.device,
-                                   seed=0 if seed is None else int(seed))
+                                   seed=0 if seed is None else int(seed), activation=act)
 
     # convenient aliases used by the tests / tools of this repository
     pi = property(lambda self: nn.Sequential(*self.policy.mlp_extractor.policy_net, self.policy.action_net))

@@ -267,7 +267,7 @@ def euler(env: OracleEnv, ws, act, dist=None):
 
 
 # ------------------------------------------------------------------------------------------------ policy (row f1)
-def policy_forward(weights, biases, obs, bf16=False):
+def policy_forward(weights, biases, obs, bf16=False, activation="relu"):
     """The controller MLP on the CPU: the float32 restatement of `c_code/neural_network.c:397-430`, or (``bf16``)
     the same network with the B200 tensor-core path's operand rounding."""
     L = lib()
@@ -279,10 +279,13 @@ def policy_forward(weights, biases, obs, bf16=False):
     wp = (_fp * nl)(*[_f(w) for w in ws])
     bp = (_fp * nl)(*[_f(b) for b in bs])
     out = np.empty((n, weights[-1].shape[0]), np.float32)
+    L.qo_set_policy_activation.argtypes = [C.c_int]
+    L.qo_set_policy_activation(1 if activation == "tanh" else 0)
     fn = L.qo_policy_forward_bf16 if bf16 else L.qo_policy_forward
     fn.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(_fp), C.POINTER(_fp), _fp, C.c_int64, _fp]
     fn.restype = None
     fn(nl, dims, wp, bp, _f(obs), n, _f(out))
+    L.qo_set_policy_activation(0)
     return out
 
 

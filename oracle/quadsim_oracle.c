@@ -435,6 +435,10 @@ void qo_apply_reset(const qo_params *p, int64_t n, float *ws, float *dist, int64
  * W[l] is row-major [out][in].  dims = {in, hidden, ..., hidden, out} (n_layers + 1 entries).
  * Pinned by tests/test_policy_oracle.py against oracle/_ref/libnn_policy_ref.so (the reference's own C, compiled
  * where it lies) through tests/golden/policy_k4.npz. */
+static int qo_policy_activation = 0; /* 0 = ReLU (`nn_relu`), 1 = tanh (`nn_tanh`, c_code/neural_network.c:413-417) */
+void qo_set_policy_activation(int act) { qo_policy_activation = act; }
+static inline float qo_act(float a) { return qo_policy_activation ? tanhf(a) : fmaxf(0.0f, a); }
+
 void qo_policy_forward(int n_layers, const int *dims, const float *const *W, const float *const *b, const float *obs,
                        int64_t n, float *out) {
 #pragma omp parallel for schedule(static)
@@ -446,7 +450,7 @@ void qo_policy_forward(int n_layers, const int *dims, const float *const *W, con
             for (int o = 0; o < on; ++o) {
                 float acc = b[l][o];
                 for (int k = 0; k < in; ++k) acc += cur[k] * W[l][(size_t)o * in + k];
-                nxt[o] = (l + 1 < n_layers) ? fmaxf(0.0f, acc) : acc;
+                nxt[o] = (l + 1 < n_layers) ? qo_act(acc) : acc;
             }
             for (int o = 0; o < on; ++o) cur[o] = nxt[o];
         }
@@ -478,7 +482,7 @@ void qo_policy_forward_bf16(int n_layers, const int *dims, const float *const *W
                 double acc = (double)qo_bf16(b[l][o]);
                 for (int k = 0; k < in; ++k) acc += (double)cur[k] * (double)qo_bf16(W[l][(size_t)o * in + k]);
                 const float a = (float)acc;
-                nxt[o] = (l + 1 < n_layers) ? qo_bf16(fmaxf(0.0f, a)) : a;
+                nxt[o] = (l + 1 < n_layers) ? qo_bf16(qo_act(a)) : a;
             }
             for (int o = 0; o < on; ++o) cur[o] = nxt[o];
         }

@@ -40,6 +40,47 @@ def test_forward_matches_reference_network(n):
     np.testing.assert_array_equal(act.cpu().numpy(), np.clip(m, -1, 1))  # deterministic: clip only (`nn_controller.c:171-173`)
 
 
+@pytest.mark.parametrize("in_dim,hidden,n_hidden", [(24, 120, 3), (24, 64, 2), (17, 96, 1)])
+def test_tanh_activation(in_dim, hidden, n_hidden, tracks):
+    """SB3's default `activation_fn` (Tanh; the reference's generated C has `nn_tanh`, c_code/neural_network.c:413-417)
+    in the policy kernel and in the fused rollout kernel: MUFU.TANH against the oracle's tanhf + BF16 rounding."""
+    import torch
+    import optimal_quad_control_rl_b200 as Q
+    from oracle import c_oracle as O
+    rng = np.random.default_rng(hidden)
+    dims = [in_dim] + [hidden] * n_hidden + [4]
+    w = [rng.normal(0, 1 / np.sqrt(dims[l]), (dims[l + 1], dims[l])).astype(np.float32) for l in range(len(dims) - 1)]
+    b = [rng.normal(0, 0.1, dims[l + 1]).astype(np.float32) for l in range(len(dims) - 1)]
+    pol = Q.MlpPolicy(w, b, activation="tanh")
+    n = 1000
+    x = rng.normal(0, 1, (n, in_dim)).astype(np.float32)
+    mean = torch.empty((n, 4), device="cuda")
+    pol.forward(torch.from_numpy(x).cuda(), deterministic=True, mean_out=mean)
+    m = mean.cpu().numpy()
+    y16 = O.policy_forward(w, b, x, bf16=True, activation="tanh")
+    y32 = O.policy_forward(w, b, x, activation="tanh")
+    print("tanh: max abs err vs bf16 oracle %.2e, vs f32 %.2e" % (np.abs(m - y16).max(), np.abs(m - y32).max()))
+    assert np.abs(m - y16).max() < 6e-3 and np.abs(m - y32).max() < 3e-2
+    assert np.abs(y32 - O.policy_forward(w, b, x)).max() > 0.05           # and it is not the ReLU network
+    with pytest.raises(Q._lib.QuadsimError if hasattr(Q, "_lib") else Exception):
+        Q.MlpPolicy([np.zeros((127, 24), np.float32), np.zeros((4, 127), np.float32)],
+                    [np.zeros(127, np.float32), np.zeros(4, np.float32)], activation="tanh")  # hidden > 120
+    if in_dim == 24:  # the fused closed loop uses the same epilogue: fused == unfused, bit for bit
+        gp, gy, sp = tracks["e2e"]
+        outs = []
+        for fused in (True, False):
+            env = Q.Quadcopter3DGates(2048, gp, gy, sp, gates_ahead=1, reset_rng="device", seed=2)
+            env.disturbance_ranges = Q.training_disturbance_ranges()
+            p2 = Q.MlpPolicy(w, b, std=np.full(4, 0.3, np.float32), activation="tanh", seed=4)
+            env.reset_tensor()
+            r = env.rollout(p2, 12, fused=fused)
+            torch.cuda.synchronize()
+            outs.append((r["obs"].clone(), r["actions"].clone(), r["rewards"].clone()))
+            env.close()
+        for a, c in zip(*outs):
+            assert torch.equal(a, c)
+
+
 @pytest.mark.parametrize("in_dim,hidden,n_hidden", [(17, 120, 3), (20, 64, 1), (28, 127, 2), (32, 96, 4)])
 def test_other_shapes_random_weights(in_dim, hidden, n_hidden):
     """INDI observation width (17: scalar loads), other gates_ahead, other depths / widths."""
