@@ -156,14 +156,13 @@ static void refresh_params(qs_env *e) {
     }
 }
 
+#define QS_STEP_FN(V, H) \
+    (e->stages == 3 ? (const void *)qs::step_kernel<V, 3, H> : e->stages == 4 ? (const void *)qs::step_kernel<V, 4, H> : (const void *)qs::step_kernel<V, 2, H>)
 static const void *step_function(const qs_env *e) {
-    const bool e2e = e->variant == QS_E2E;
-    switch (e->stages) {
-        case 3: return e2e ? (const void *)qs::step_kernel<qs::kE2E, 3> : (const void *)qs::step_kernel<qs::kINDI, 3>;
-        case 4: return e2e ? (const void *)qs::step_kernel<qs::kE2E, 4> : (const void *)qs::step_kernel<qs::kINDI, 4>;
-        default: return e2e ? (const void *)qs::step_kernel<qs::kE2E, 2> : (const void *)qs::step_kernel<qs::kINDI, 2>;
-    }
+    if (e->variant == QS_E2E) return e->l2_hints ? QS_STEP_FN(qs::kE2E, true) : QS_STEP_FN(qs::kE2E, false);
+    return e->l2_hints ? QS_STEP_FN(qs::kINDI, true) : QS_STEP_FN(qs::kINDI, false);
 }
+#undef QS_STEP_FN
 
 static size_t smem_bytes(const qs_env *e) {
     return ((size_t)qs::kBlock * e->obs_len + (size_t)e->n_gates * qs::kTrackRow) * sizeof(float);
@@ -701,6 +700,7 @@ struct qs_policy {
     unsigned char *w_dev = nullptr;
     unsigned long long *epoch_dev = nullptr;
     bool dirty = true, pdl = true;
+    bool ts = true;      // qs_policy_forward runs policy_kernel_ts (activations in tensor memory); QS_POLICY_TS=0: policy_kernel
     int activation = 0;  // 0 ReLU, 1 tanh
     uint64_t seed = 0, launches = 0;
     int64_t env_offset = 0;
@@ -785,6 +785,12 @@ int qs_policy_create(qs_policy **out, int in_dim, int n_hidden, int hidden_dim, 
     if ((c = cudaMemset(p->epoch_dev, 0, 16)) != cudaSuccess) return bail(c, "cudaMemset");
     if ((c = cudaFuncSetAttribute((const void *)qs::policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem)) != cudaSuccess)
         return bail(c, "cudaFuncSetAttribute(policy smem)");
+    // forward-only launches: the kernel that keeps the activations in tensor memory (quadsim_policy.cuh, policy_kernel_ts)
+    if (const char *tv = getenv("QS_POLICY_TS")) p->ts = atoi(tv) != 0;
+    if (qs::policy_ts_smem_bytes(p->k1, n_hidden) > (size_t)smem_max) p->ts = false;
+    if (p->ts && (c = cudaFuncSetAttribute((const void *)qs::policy_kernel_ts, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)qs::policy_ts_smem_bytes(p->k1, n_hidden))) != cudaSuccess)
+        return bail(c, "cudaFuncSetAttribute(policy_ts smem)");
     if (const char *pv = getenv("QS_PDL")) p->pdl = atoi(pv) != 0;
     p->grid = sms;
     *out = p;
@@ -868,17 +874,18 @@ static int policy_launch(qs_policy *p, const float *obs_dev, int64_t n, float *a
     const long long tiles = (n + qs::kPolRows - 1) / qs::kPolRows;
     void *args[] = {&P};
     cudaLaunchConfig_t cfg{};
-    const long long ctas = (tiles + p->groups - 1) / p->groups;
+    const int per_cta = p->ts ? qs::kTsChains : p->groups;  // 128-row tiles in flight per CTA
+    const long long ctas = (tiles + per_cta - 1) / per_cta;
     cfg.gridDim = dim3((unsigned)(ctas < p->grid ? ctas : p->grid));
-    cfg.blockDim = dim3((unsigned)(qs::kPolRows * p->groups));
-    cfg.dynamicSmemBytes = p->smem;
+    cfg.blockDim = dim3((unsigned)(p->ts ? qs::kTsChains * qs::kTsThreads : qs::kPolRows * p->groups));
+    cfg.dynamicSmemBytes = p->ts ? qs::policy_ts_smem_bytes(p->k1, p->n_hidden) : p->smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = p->pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t c = cudaLaunchKernelExC(&cfg, (const void *)qs::policy_kernel, args);
+    cudaError_t c = cudaLaunchKernelExC(&cfg, p->ts ? (const void *)qs::policy_kernel_ts : (const void *)qs::policy_kernel, args);
     if (c != cudaSuccess) { p->err = std::string("policy_kernel launch: ") + cudaGetErrorString(c); return QS_ERR_CUDA; }
     p->launches++;
     return QS_OK;

@@ -117,6 +117,12 @@ __device__ __forceinline__ float norm3_rn(float a, float b, float c) {
 // yaw %= 2*pi ; yaw[yaw > pi] -= 2*pi ; yaw[yaw < -pi] += 2*pi   in float32 (`:393-396`).
 // floor-quotient + one FMA reproduces np.remainder exactly: a - n*b is a multiple of ulp(b) below b, hence
 // representable, and for |a| < b both sides perform the same single rounded add.
+__device__ __noinline__ float wrap_yaw_slow(float a) {  // blown-up state: exact, out of line
+    const float b = 6.283185307179586f;
+    float m = fmodf(a, b);
+    if (m < 0.0f) m = add_rn(m, b);
+    return m;
+}
 __device__ __forceinline__ float wrap_yaw(float a) {
     const float b = 6.283185307179586f, pi = 3.141592653589793f;
     float m;
@@ -125,9 +131,8 @@ __device__ __forceinline__ float wrap_yaw(float a) {
         m = fmaf(-n, b, a);
         if (m < 0.0f) m = add_rn(m, b);
         if (m >= b) m = sub_rn(m, b);
-    } else {  // blown-up state: exact but slow path
-        m = fmodf(a, b);
-        if (m < 0.0f) m = add_rn(m, b);
+    } else {
+        m = wrap_yaw_slow(a);
     }
     if (m > pi) m = sub_rn(m, b);
     if (m < -pi) m = add_rn(m, b);
@@ -287,41 +292,51 @@ __device__ __forceinline__ void draw_reset_warp(const StepParams &P, long long w
     __syncwarp();
 }
 
-// update_states_gate for one env (`:365-450`), written to a row in shared memory.
+// update_states_gate for one env (`:365-450`): the gate-frame part of the row (position, horizontal velocity, yaw)
+struct ObsHead { float o0, o1, o2, o3, o4, yaw; };
 template <int V>
-__device__ __forceinline__ void write_obs(const StepParams &P, const float *s_track, const EnvState<V> &e,
-                                          uint32_t tg, float *o) {
-    const int ng = P.n_gates;
+__device__ __forceinline__ ObsHead obs_head(const float *s_track, const EnvState<V> &e, uint32_t tg) {
     const float4 ga = *reinterpret_cast<const float4 *>(s_track + tg * kTrackRow);
     const float2 gb = *reinterpret_cast<const float2 *>(s_track + tg * kTrackRow + 4);
     const float c = gb.x, sn = gb.y;
     const float dx = sub_rn(e.x, ga.x), dy = sub_rn(e.y, ga.y);
-    const float o0 = add_rn(mul_rn(dx, c), mul_rn(dy, sn));
-    const float o1 = add_rn(mul_rn(dx, -sn), mul_rn(dy, c));
-    const float o2 = sub_rn(e.z, ga.z);
-    const float o3 = add_rn(mul_rn(e.vx, c), mul_rn(e.vy, sn));
-    const float o4 = add_rn(mul_rn(e.vx, -sn), mul_rn(e.vy, c));
-    const float yaw = wrap_yaw(sub_rn(e.psi, ga.w));
+    ObsHead h;
+    h.o0 = add_rn(mul_rn(dx, c), mul_rn(dy, sn));
+    h.o1 = add_rn(mul_rn(dx, -sn), mul_rn(dy, c));
+    h.o2 = sub_rn(e.z, ga.z);
+    h.o3 = add_rn(mul_rn(e.vx, c), mul_rn(e.vy, sn));
+    h.o4 = add_rn(mul_rn(e.vx, -sn), mul_rn(e.vy, c));
+    h.yaw = wrap_yaw(sub_rn(e.psi, ga.w));
+    return h;
+}
+__device__ __forceinline__ float dist_obs(const StepParams &P, float d, int k) {
+    return fmaf(sub_rn(sub_rn(d, P.obs_lo[k]), P.obs_lo2[k]), P.obs_scale[k], -1.0f);
+}
+// ... written to a row in shared memory (16-byte aligned for E2E: obs_len is a multiple of 4 there)
+template <int V>
+__device__ __forceinline__ void write_obs(const StepParams &P, const float *s_track, const EnvState<V> &e,
+                                          uint32_t tg, float *o) {
+    const int ng = P.n_gates;
+    const ObsHead h = obs_head<V>(s_track, e, tg);
     if (V == kE2E) {
         float4 *o4p = reinterpret_cast<float4 *>(o);
-        o4p[0] = make_float4(o0, o1, o2, o3);
-        o4p[1] = make_float4(o4, e.vz, e.phi, e.th);
-        o4p[2] = make_float4(yaw, e.p, e.q, e.r);
+        o4p[0] = make_float4(h.o0, h.o1, h.o2, h.o3);
+        o4p[1] = make_float4(h.o4, e.vz, e.phi, e.th);
+        o4p[2] = make_float4(h.yaw, e.p, e.q, e.r);
         o4p[3] = make_float4(e.w[0], e.w[1], e.w[2], e.w[V == kE2E ? 3 : 0]);
         uint32_t nx = tg;
+#pragma unroll 1
         for (int i = 0; i < P.gates_ahead; ++i) {
             nx = (nx + 1 == (uint32_t)ng) ? 0u : nx + 1;
             o4p[4 + i] = *reinterpret_cast<const float4 *>(s_track + nx * kTrackRow + 8);
         }
-        o4p[4 + P.gates_ahead] = make_float4(
-            fmaf(sub_rn(sub_rn(e.dist[0], P.obs_lo[0]), P.obs_lo2[0]), P.obs_scale[0], -1.0f),
-            fmaf(sub_rn(sub_rn(e.dist[1], P.obs_lo[1]), P.obs_lo2[1]), P.obs_scale[1], -1.0f),
-            fmaf(sub_rn(sub_rn(e.dist[2], P.obs_lo[2]), P.obs_lo2[2]), P.obs_scale[2], -1.0f),
-            fmaf(sub_rn(sub_rn(e.dist[5], P.obs_lo[3]), P.obs_lo2[3]), P.obs_scale[3], -1.0f));
+        o4p[4 + P.gates_ahead] = make_float4(dist_obs(P, e.dist[0], 0), dist_obs(P, e.dist[1], 1), dist_obs(P, e.dist[2], 2),
+                                             dist_obs(P, e.dist[5], 3));
     } else {
-        o[0] = o0; o[1] = o1; o[2] = o2; o[3] = o3; o[4] = o4; o[5] = e.vz; o[6] = e.phi; o[7] = e.th;
-        o[8] = yaw; o[9] = e.p; o[10] = e.q; o[11] = e.r; o[12] = e.w[0];
+        o[0] = h.o0; o[1] = h.o1; o[2] = h.o2; o[3] = h.o3; o[4] = h.o4; o[5] = e.vz; o[6] = e.phi; o[7] = e.th;
+        o[8] = h.yaw; o[9] = e.p; o[10] = e.q; o[11] = e.r; o[12] = e.w[0];
         uint32_t nx = tg;
+#pragma unroll 1
         for (int i = 0; i < P.gates_ahead; ++i) {
             nx = (nx + 1 == (uint32_t)ng) ? 0u : nx + 1;
             const float4 rel = *reinterpret_cast<const float4 *>(s_track + nx * kTrackRow + 8);
@@ -329,7 +344,6 @@ __device__ __forceinline__ void write_obs(const StepParams &P, const float *s_tr
         }
     }
 }
-
 // The block's observation tile [rows][obs_len] is contiguous in global memory: one TMA bulk store moves it.
 __device__ __forceinline__ void store_obs_tile(float *dst, const float *s_obs, int rows, int obs_len) {
     const uint32_t bytes = (uint32_t)rows * (uint32_t)obs_len * 4u;
@@ -687,14 +701,14 @@ __host__ __device__ constexpr size_t step_smem_bytes(int variant, int stages, in
 }
 
 // lane 0 of a warp: fill one of the warp's stages with the 32 envs starting at `first`
-template <int V>
+template <int V, bool kHints>
 __device__ __forceinline__ void issue_warp_tile(const StepParams &P, unsigned char *st, uint64_t *bar, long long first,
                                                 uint64_t pol_state, uint64_t pol_stream) {
     using S = Stage<V>;
     const long long rem = P.n - first;
     const uint32_t act_bytes = rem >= 32 ? 512u : (rem > 0 ? (uint32_t)rem * 16u : 0u);  // caller's buffer is not padded
     mbar_expect_tx(bar, (uint32_t)Blk<V>::BYTES + act_bytes);
-    if (P.l2_hints) {
+    if (kHints) {
         bulk_load_hint(st, P.s.base + (first >> 5) * (long long)Blk<V>::BYTES, Blk<V>::BYTES, bar,
                        (first >> 5) < P.keep_blocks ? pol_state : pol_stream);
         if (act_bytes) bulk_load_hint(st + S::ACT, P.actions + first, act_bytes, bar, pol_stream);
@@ -709,15 +723,20 @@ __device__ __forceinline__ void issue_warp_tile(const StepParams &P, unsigned ch
 // loads the moment the warp has copied it to registers, and waits on the stage's mbarrier for the bytes to land.
 // There is no block barrier anywhere in the loop, so the warps of an SM drift apart: while one computes, others
 // load or store.  Observations leave through the warp's slice of the staging tile as one TMA bulk store (32 rows
-// of a row-major (N,D) array are contiguous).
+// of a row-major (N,D) array are contiguous).  kHints: the L2 residency policies (see l2_policy_*) are compiled in.
 constexpr int kStepThreads = kBlock;
 
-template <int V, int kStages>
+template <int V, int kStages, bool kHints>
 __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel(const __grid_constant__ StepParams P) {
     using S = Stage<V>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
+    // INDI: the shuffle tells the compiler that `warp` is warp-uniform, so everything derived from it (stage, barrier,
+    // block and tile addresses) is computed once per warp on the uniform datapath and the TMA issues need no per-lane
+    // address loop: 33.6 -> 31.0 us per step at N = 2^20.  E2E, whose arithmetic already fills the issue slots between
+    // the address chains, measured 1 % slower with it (58.2 -> 58.8 us; profiles/r2/step_kernel_ablation.md).
+    const int lane = tid & 31;
+    const int warp = (V == kINDI) ? __shfl_sync(0xffffffffu, tid >> 5, 0) : (tid >> 5);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw) + warp * kStages;          // this warp's barriers
     unsigned char *stages = smem_raw + kBarBytes + warp * (kStages * S::BYTES);          // this warp's ring
     float *s_obs = reinterpret_cast<float *>(smem_raw + kBarBytes + kWarps * kStages * S::BYTES);
@@ -731,8 +750,7 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < P.n_gates * kTrackRow; i += kStepThreads) s_track[i] = P.track[i];
-    const bool hints = P.l2_hints != 0;
-    const uint64_t pol_keep = hints ? l2_policy_evict_last() : 0ull, pol_stream = hints ? l2_policy_evict_first() : 0ull;
+    const uint64_t pol_keep = kHints ? l2_policy_evict_last() : 0ull, pol_stream = kHints ? l2_policy_evict_first() : 0ull;
     __syncthreads();  // barrier init and track table visible to everyone
     // Everything above touched only launch constants.  From here on we read and write simulator state that the
     // previous step's grid may still be producing (programmatic dependent launch).
@@ -742,7 +760,7 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
 #pragma unroll
         for (int s = 0; s < kStages; ++s) {
             const long long t = tile0 + (long long)s * gridDim.x;
-            if (t < n_tiles) issue_warp_tile<V>(P, stages + s * S::BYTES, &full[s], t * kBlock + warp * 32, pol_keep, pol_stream);
+            if (t < n_tiles) issue_warp_tile<V, kHints>(P, stages + s * S::BYTES, &full[s], t * kBlock + warp * 32, pol_keep, pol_stream);
         }
     }
 
@@ -750,8 +768,9 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
     float reward_acc = 0.0f;  // stats are reduced once per CTA lifetime, not per tile
     unsigned c_act = 0, c_done = 0, c_tr = 0, c_gp = 0, c_gc = 0, c_gr = 0, c_ob = 0;
     const bool write_obs_tile = P.mode != kModePause;
+    const bool fused_reset = P.mode == kModeNormal && P.reset_source == kResetDevice;
     float *const my_obs = s_obs + tid * P.obs_len;
-    const float *const warp_obs = s_obs + warp * 32 * P.obs_len;
+    float *const warp_obs = s_obs + warp * 32 * P.obs_len;
     bool obs_in_flight = false;  // warp-uniform: a bulk store of this warp's observation slice may still be reading it
     int it = 0;
     for (long long tile = tile0; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -786,7 +805,7 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
         __syncwarp();  // the warp's inputs are in registers: refill the stage with the tile kStages ahead
         if (lane == 0) {
             const long long nt = tile + (long long)kStages * gridDim.x;
-            if (nt < n_tiles) issue_warp_tile<V>(P, st, &full[stage], nt * kBlock + warp * 32, pol_keep, pol_stream);
+            if (nt < n_tiles) issue_warp_tile<V, kHints>(P, st, &full[stage], nt * kBlock + warp * 32, pol_keep, pol_stream);
         }
 
 #ifdef QS_EXP_NOCOMPUTE  // experiment only: the memory pipeline alone (same loads and stores, no arithmetic)
@@ -800,34 +819,31 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
 
         // ---- branch logic (`:568-585`)
         bool write_world = active, write_dist = false;
-        if (P.mode == kModeNormal) {
-            if (P.reset_source == kResetDevice) {  // warp-uniform branch: the whole warp takes part in the draw
+        if (fused_reset) {  // warp-uniform branch: the whole warp takes part in the draw
 #ifdef QS_EXP_NORESET  // experiment only: what the fused reset path costs
-                const bool need = false;
+            const bool need = false;
 #else
-                const bool need = dn && active;
+            const bool need = dn && active;
 #endif
-                // scratch = the head of this warp's observation slice: its previous bulk store must have been read
-                if (__any_sync(0xffffffffu, need)) {
-                    if (lane == 0 && obs_in_flight) bulk_store_wait_read();
-                    obs_in_flight = false;
-                    __syncwarp();
-                    draw_reset_warp<V>(P, base + warp * 32, need, reinterpret_cast<uint4 *>(s_obs + warp * 32 * P.obs_len), n,
-                                       load_epoch(P.epoch));
-                }
-                if (need) {
-                    tg = 0; sc = 0;
-                    write_dist = (V == kE2E);
-                }
+            // scratch = the head of this warp's observation slice: its previous bulk store must have been read
+            if (__any_sync(0xffffffffu, need)) {
+                if (lane == 0 && obs_in_flight) bulk_store_wait_read();
+                obs_in_flight = false;
+                __syncwarp();
+                draw_reset_warp<V>(P, base + warp * 32, need, reinterpret_cast<uint4 *>(warp_obs), n, load_epoch(P.epoch));
+            }
+            if (need) {
+                tg = 0; sc = 0;
+                write_dist = (V == kE2E);
             }
         } else if (P.mode == kModePauseIfCollision) {
             if (dn) { n = e; write_world = false; }
-        } else {  // env.pause
+        } else if (P.mode == kModePause) {
             write_world = false;
         }
         unsigned char *const gblk = P.s.base + (tile * kWarps + warp) * (long long)Blk<V>::BYTES;  // this warp's block
         const uint8_t dn8 = (P.mode == kModePause) ? (uint8_t)0 : (uint8_t)(dn ? 1 : 0);
-        if (!hints) {
+        if (!kHints) {
             if (active) {
                 reinterpret_cast<uint32_t *>(gblk + S::META)[lane] = (tg << 24) | sc;
                 P.rew[env] = reward;
@@ -889,17 +905,21 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0 && bytes) {
-                    if (hints) bulk_store_hint(dst, warp_obs, bytes, pol_stream);
+                    if (kHints) bulk_store_hint(dst, warp_obs, bytes, pol_stream);
                     else bulk_store(dst, warp_obs, bytes);
+#pragma unroll 1
                     for (int p = 0; p < P.n_peers; ++p)  // NVLink: the tile leaves for every peer while the next one is computed
                         bulk_store(P.peer_obs[p] + (P.peer_row_offset + base + warp * 32) * P.obs_len, warp_obs, bytes);
                 }
                 obs_in_flight = true;
             } else {
                 __syncwarp();
+#pragma unroll 1
                 for (int i = lane; i < rows * P.obs_len; i += 32) dst[i] = warp_obs[i];
+#pragma unroll 1
                 for (int p = 0; p < P.n_peers; ++p) {
                     float *pd = P.peer_obs[p] + (P.peer_row_offset + base + warp * 32) * P.obs_len;
+#pragma unroll 1
                     for (int i = lane; i < rows * P.obs_len; i += 32) pd[i] = warp_obs[i];
                 }
                 __syncwarp();

@@ -362,6 +362,228 @@ __global__ void __launch_bounds__(4 * kPolRows, 1) policy_kernel(const __grid_co
     }
 }
 
+// ------------------------------------------------------------------------------------------------ activations in TMEM
+// policy_kernel_ts: the same network with the activations kept in TENSOR MEMORY between layers.
+//
+// Why: in policy_kernel both MMA operands come from shared memory.  An M=128, N=128, K=16 BF16 MMA reads 4 KB of A and
+// 4 KB of B in the 64 cycles it occupies the tensor pipe = the SM's whole 128 B/clk of shared-memory bandwidth, and the
+// epilogues store another 32 KB per layer and tile into the same memory: the four tile groups queue on shared memory
+// (profiles/r2/step_kernel_ablation.md section 4; the TMEM read-out, blamed in round 1, runs at 900 B/clk).
+// Here a layer's A operand lives in TMEM (tcgen05.mma with [a_tmem]; `UTCHMMA tmem[..], gdesc[..], tmem[..]`): the
+// epilogue reads the FP32 accumulator (tcgen05.ld), applies the activation, packs two BF16 per 32-bit column
+// (unit 2c in the low half: measured, profiles/microbench/umma_ts_probe.cu) and writes the next layer's A with
+// tcgen05.st -- shared memory only serves the weights (B): a third of the traffic, no bank-conflict or proxy-fence
+// concerns, and no 32 KB A buffers.
+//
+// Shape: one persistent CTA per SM, 2 tile groups ("chains") of 256 threads.  A chain owns 192 TMEM columns: 64 for A
+// (128 BF16 per row) and 128 for the accumulator; thread = (row, column half): warps w and w+4 of a group address the
+// same TMEM lane quadrant and each takes 64 of the 128 accumulator columns, so an epilogue is 2 loads + 32
+// conversions + 1 store per thread.  While one chain's epilogue runs, the other chain's MMAs do.
+constexpr int kTsThreads = 256;   // per chain
+constexpr int kTsChains = 2;
+constexpr int kTsCols = 192;      // TMEM columns per chain: A [0, 64) | D [64, 192)
+
+__host__ __device__ constexpr size_t policy_ts_smem_bytes(int k1, int n_hidden) { return 128 + policy_weight_bytes(k1, n_hidden); }
+
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t *v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+                 "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void chain_barrier(int chain) { asm volatile("bar.sync %0, 256;" ::"r"(chain + 1) : "memory"); }
+
+// 32 accumulator columns -> activation -> 16 packed BF16 words
+__device__ __forceinline__ void act_pack16(const uint32_t *v, uint32_t *w, int act) {
+    if (act == 0) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) w[c] = pack_relu_bf16(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
+    } else {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) w[c] = pack_bf16(tanh_fast(__uint_as_float(v[2 * c])), tanh_fast(__uint_as_float(v[2 * c + 1])));
+    }
+}
+
+// one thread: the K/16 MMAs of a layer, D[128 x N] (+)= A[tmem, 128 x K] . W[smem, N x K]^T
+__device__ __forceinline__ void issue_layer_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t w_smem, int k, int n_rows, uint64_t *bar) {
+    const uint32_t idesc = umma_idesc_bf16(kPolRows, n_rows);
+    const uint32_t w_slab = (uint32_t)n_rows * 16u;
+    for (int j = 0; j < k / 16; ++j)
+        umma_bf16_ts(d_tmem, a_tmem + (uint32_t)j * 8u, umma_desc(w_smem + (uint32_t)j * 2u * w_slab, w_slab, 128), idesc, j > 0);
+    umma_commit(bar);
+}
+
+// this thread's 16 observation values [16 * half, 16 * half + 16) of row `env` (zero beyond in_dim, 1 at in_dim)
+__device__ __forceinline__ void load_obs16(const PolicyParams &P, long long env, bool active, int k0, float (&x)[16]) {
+    const float *row = P.obs + env * P.in_dim;
+    const bool vec = (P.in_dim & 3) == 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int k = k0 + q * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) {
+            if (vec) {
+                if (k < P.in_dim) v = *reinterpret_cast<const float4 *>(row + k);
+            } else {
+                if (k + 0 < P.in_dim) v.x = row[k + 0];
+                if (k + 1 < P.in_dim) v.y = row[k + 1];
+                if (k + 2 < P.in_dim) v.z = row[k + 2];
+                if (k + 3 < P.in_dim) v.w = row[k + 3];
+            }
+        }
+        x[q * 4 + 0] = v.x; x[q * 4 + 1] = v.y; x[q * 4 + 2] = v.z; x[q * 4 + 3] = v.w;
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+        if (k0 + q == P.in_dim) x[q] = 1.0f;  // the constant input that multiplies the folded bias
+}
+__device__ __forceinline__ void store_obs16(uint32_t taddr, const float (&x)[16]) {
+    uint32_t w[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) w[c] = pack_bf16(x[2 * c], x[2 * c + 1]);
+    tmem_st8(taddr, w);
+}
+
+__global__ void __launch_bounds__(kTsChains * kTsThreads, 1) policy_kernel_ts(const __grid_constant__ PolicyParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar_w = reinterpret_cast<uint64_t *>(smem_raw);        // weights landed
+    uint64_t *bar_mma_all = bar_w + 1;                               // [chain]: a layer's MMAs completed
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + 64);
+    unsigned char *s_w = smem_raw + 128;
+    const int chain = threadIdx.x / kTsThreads, tid = threadIdx.x % kTsThreads;
+    const int warp = tid >> 5, quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + (tid & 31);                          // row of the tile = TMEM lane
+    uint64_t *bar_mma = bar_mma_all + chain;
+    const long long n_tiles = (P.n + kPolRows - 1) / kPolRows;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_w, 1);
+        for (int g = 0; g < kTsChains; ++g) mbar_init(bar_mma_all + g, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar_w, P.weight_bytes);
+        bulk_load(s_w, P.weights, P.weight_bytes, bar_w);  // launch constant: may precede the PDL wait
+    }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t t_chain = tmem_base + (uint32_t)chain * kTsCols;                 // lane 0 of this chain's columns
+    const uint32_t t_a = t_chain + ((uint32_t)(quad * 32) << 16);                   // this thread's lane quadrant: A columns
+    const uint32_t t_d = t_a + 64u;                                                 // ... accumulator columns
+    pdl_launch_dependents();
+    pdl_wait();  // observations come from the previous kernel on the stream (the env step)
+    mbar_wait(bar_w, 0);
+
+    const uint32_t w_smem = smem_u32(s_w);
+    const bool const_last = P.hidden <= kPolHidden - 8;
+    if (const_last && half == 1) {  // units 120..126 = padding, unit 127 = the constant 1: columns 60..63 of A, written once
+        const uint32_t c[4] = {0u, 0u, 0u, 0x3F800000u};
+        tmem_st4(t_a + 60u, c);
+    }
+    const unsigned long long epoch = P.deterministic ? 0ull : *reinterpret_cast<const volatile unsigned long long *>(P.epoch);
+    const long long stride = (long long)gridDim.x * kTsChains;
+    const bool pre = P.k1 == 32;  // the common widths (in_dim <= 31): the next tile's row is fetched a whole tile ahead
+    float nx[16];
+    {
+        const long long tile = (long long)blockIdx.x * kTsChains + chain;
+        if (pre && tile < n_tiles) load_obs16(P, tile * kPolRows + row, tile * kPolRows + row < P.n, 16 * half, nx);
+    }
+    uint32_t phase = 0;
+    for (long long tile = (long long)blockIdx.x * kTsChains + chain; tile < n_tiles; tile += stride) {
+        const long long env = tile * kPolRows + row;
+        const bool active = env < P.n;
+        // ---- A operand of layer 1: the observation row, BF16, two values per TMEM column; thread = (row, 16 columns)
+        if (pre) {
+            store_obs16(t_a + 8u * (uint32_t)half, nx);
+        } else {
+            for (int k0 = 16 * half; k0 < P.k1; k0 += 32) {
+                float x[16];
+                load_obs16(P, env, active, k0, x);
+                store_obs16(t_a + (uint32_t)(k0 >> 1), x);
+            }
+        }
+        tmem_st_wait();
+        uint32_t w_off = 0;
+        for (int layer = 0; layer <= P.n_hidden; ++layer) {
+            const bool last = layer == P.n_hidden;
+            const int k = layer == 0 ? P.k1 : kPolHidden;
+            // A (tcgen05.st, waited for) and the accumulator reads of the previous epilogue are ordered before the MMAs
+            tc_fence_before();
+            chain_barrier(chain);
+            if (tid == 0) {
+                tc_fence_after();
+                issue_layer_ts(t_chain + 64u, t_chain, w_smem + w_off, k, last ? kPolOut : kPolHidden, bar_mma);
+            }
+            if (layer == 0 && pre) {  // the loads fly while the chain computes
+                const long long nenv = env + stride * kPolRows;
+                if (tile + stride < n_tiles) load_obs16(P, nenv, nenv < P.n, 16 * half, nx);
+            }
+            w_off += layer == 0 ? policy_w1_bytes(P.k1) : policy_wh_bytes();
+            mbar_wait(bar_mma, phase);
+            phase ^= 1u;
+            tc_fence_after();
+            if (!last) {
+                // ---- epilogue: accumulator columns [64 half, 64 half + 64) -> activation -> A columns [32 half, 32 half + 32)
+                uint32_t v0[32], v1[32], w[32];
+                tmem_ld32(t_d + 64u * (uint32_t)half, v0);
+                tmem_ld32(t_d + 64u * (uint32_t)half + 32u, v1);
+                tmem_ld_wait();
+                act_pack16(v0, w, P.activation);
+                act_pack16(v1, w + 16, P.activation);
+                if (half == 1 && const_last) {  // columns 60..63 keep the constant
+                    tmem_st16(t_a + 32u, w);
+                    tmem_st8(t_a + 48u, w + 16);
+                    tmem_st4(t_a + 56u, w + 24);
+                } else {
+                    tmem_st16(t_a + 32u * (uint32_t)half, w);
+                    tmem_st16(t_a + 32u * (uint32_t)half + 16u, w + 16);
+                }
+                tmem_st_wait();
+            } else if (half == 0) {
+                uint32_t v[8];
+                tmem_ld8(t_d, v);
+                tmem_ld_wait();
+                float a[4] = {__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])};
+                if (active) {
+                    if (P.mean) *reinterpret_cast<float4 *>(P.mean + env * 4) = make_float4(a[0], a[1], a[2], a[3]);
+                    if (!P.deterministic) add_exploration_noise(P, env, epoch, a);
+                    if (P.raw) *reinterpret_cast<float4 *>(P.raw + env * 4) = make_float4(a[0], a[1], a[2], a[3]);
+#pragma unroll
+                    for (int k2 = 0; k2 < 4; ++k2) a[k2] = fminf(fmaxf(a[k2], -1.0f), 1.0f);  // `nn_controller.c:171-173`
+                    *reinterpret_cast<float4 *>(P.actions + env * 4) = make_float4(a[0], a[1], a[2], a[3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (threadIdx.x == 0 && !P.deterministic) {  // advance the noise epoch once per launch (same protocol as the step kernel)
+        __threadfence();
+        if (atomicAdd(P.epoch + 1, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+            P.epoch[1] = 0;
+            P.epoch[0] = P.epoch[0] + 1;
+        }
+    }
+}
+
 
 // Generalised advantage estimation over a device-resident rollout (SB3 `RolloutBuffer.compute_returns_and_advantage`,
 // the step after `collect_rollouts` in `model.learn`, `3D quad race.ipynb:820`): one thread per env walks its column

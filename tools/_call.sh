@@ -1,6 +1,7 @@
-timeout 300 python -m pytest tests/test_gpu_policy.py tests/test_gpu_rollout_fused.py tests/test_gpu_ppo.py -q 2>&1 | tail -5
-python tools/_probe_nvlink.py 2>&1 | tail -12
-bash tools/gpu.sh numpy c6
-bash tools/gpu.sh ncu c6
-bash tools/gpu.sh ncu-tc c6
-bash tools/gpu.sh bench c6
+B="python bench.py --steps 1000 --warmup 100 --no-cpu-baseline --no-configs --e2e-steps 3"
+source <(sed -n '/^line()/,/^}/p' tools/gpu.sh)
+{ for lib in head "" nouni head "" nouni; do
+  QS_LIB=${lib:+build/exp/libquadsim_$lib.so} $B 2>/dev/null | line "e2e ${lib:-product}"
+  QS_LIB=${lib:+build/exp/libquadsim_$lib.so} $B --variant indi 2>/dev/null | line "indi ${lib:-product}"
+done; } 2>&1 | tee gpurun_out/d4_variants.log
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/d4_pytest.log

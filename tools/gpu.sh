@@ -29,14 +29,7 @@ if 'cpu_baseline' in d: print('    cpu', d['cpu_baseline']['kind'], '%.4g' % d['
 }
 Q="--no-cpu-baseline --no-configs --e2e-steps 3"
 case $cmd in
-build-ncu-train)
-  ncu --set full --import-source on --clock-control none -k regex:ppo_grad_kernel -s 30 -c 1 -o gpurun_out/${tag}_ppo_grad -f \
-      python tools/train_ppo.py --num-envs 65536 --iterations 2 --update fused > gpurun_out/${tag}_ncu_train.log 2>&1
-  ncu --metrics gpu__time_duration.sum --clock-control none -k regex:ppo_ -s 200 -c 40 --csv --log-file gpurun_out/${tag}_train_launches.csv \
-      python tools/train_ppo.py --num-envs 65536 --iterations 2 --update fused > /dev/null 2>&1
-  ls -la gpurun_out/${tag}_*.ncu-rep
-  ;;
-variants)
+build-variants)
   mkdir -p build/exp
   python - "$tag" "$@" <<'PY'
 import sys; sys.path.insert(0, '.')
