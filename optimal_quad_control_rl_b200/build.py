@@ -15,7 +15,7 @@ HEADERS = [os.path.join(CSRC, h) for h in ("quadsim_kernels.cuh", "quadsim_polic
           [os.path.join(ROOT, "include", "quadsim.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include")]
+              "-Xcompiler", "-fPIC,-fopenmp", "-shared", "-I" + os.path.join(ROOT, "include"), "-lgomp"]
 
 
 def nvcc_path():

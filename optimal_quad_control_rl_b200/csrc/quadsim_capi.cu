@@ -12,6 +12,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "quadsim.h"
@@ -44,6 +45,7 @@ struct qs_env {
     // staging for the host-buffer entry points
     float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr;
     float *act_stage = nullptr;  // pinned host staging for pageable / float64 actions (qs_step_host_ex)
+    int host_threads = 1;        // OpenMP threads that fill it
     unsigned long long *info_dev = nullptr, *info_host = nullptr;  // step_info_kernel result (3 words) + its pinned copy
     cudaEvent_t ev_info = nullptr;
     uint8_t *h_done = nullptr, *h_flags = nullptr;
@@ -575,6 +577,11 @@ static int ensure_io(qs_env *e) {
     QS_CUDA(e, cudaEventCreateWithFlags(&e->ev_k, cudaEventDisableTiming));
     QS_CUDA(e, cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
     if (const char *cv = getenv("QS_HOST_CHUNKS")) { int v = atoi(cv); if (v >= 1 && v <= 64) e->host_chunks = v; }
+    {   // staging threads of qs_step_host_ex: a few are enough to outrun PCIe; QS_HOST_THREADS overrides
+        const unsigned hc = std::thread::hardware_concurrency();
+        e->host_threads = hc >= 16 ? 6 : (hc >= 4 ? (int)hc / 2 : 1);
+        if (const char *tv = getenv("QS_HOST_THREADS")) { int v = atoi(tv); if (v >= 1 && v <= 64) e->host_threads = v; }
+    }
     return QS_OK;
 }
 
@@ -621,12 +628,20 @@ int qs_step_host_ex(qs_env *e, const void *act, int act_dtype, float *obs, float
         const size_t cnt = (size_t)((t1 * qs::kBlock < e->n ? t1 * qs::kBlock : e->n)) - first;
         const float *src = (const float *)act + first * 4;
         if (stage) {  // the previous step's uploads completed before that call returned: the staging buffer is free
+            // a few host threads per chunk: one core copies ~8 GB/s, the 16 MB of a 2^20-env action array would cost
+            // as much as the whole PCIe transfer of the results
             float *dst = e->act_stage + first * 4;
-            if (act_dtype == QS_F64) {
-                const double *s64 = (const double *)act + first * 4;
-                for (size_t i = 0; i < cnt * 4; ++i) dst[i] = (float)s64[i];
-            } else {
-                memcpy(dst, src, cnt * 16);
+            const long long pieces = (long long)((cnt * 16 + 262143) / 262144);  // 256 KB per piece
+            const int threads = (int)(pieces < e->host_threads ? pieces : e->host_threads);
+#pragma omp parallel for num_threads(threads) schedule(static) if (threads > 1)
+            for (long long p = 0; p < pieces; ++p) {
+                const size_t a = (size_t)p * 16384, b = a + 16384 < cnt ? a + 16384 : cnt;  // envs [a, b) of this chunk
+                if (act_dtype == QS_F64) {
+                    const double *s64 = (const double *)act + first * 4;
+                    for (size_t i = a * 4; i < b * 4; ++i) dst[i] = (float)s64[i];
+                } else {
+                    memcpy(dst + a * 4, src + a * 4, (b - a) * 16);
+                }
             }
             src = dst;
         }
@@ -700,7 +715,7 @@ struct qs_policy {
     unsigned char *w_dev = nullptr;
     unsigned long long *epoch_dev = nullptr;
     bool dirty = true, pdl = true;
-    bool ts = true;      // qs_policy_forward runs policy_kernel_ts (activations in tensor memory); QS_POLICY_TS=0: policy_kernel
+    bool ts = false;     // QS_POLICY_TS=1: qs_policy_forward runs policy_kernel_ts (activations in tensor memory; measured slower: 2 chains)
     int activation = 0;  // 0 ReLU, 1 tanh
     uint64_t seed = 0, launches = 0;
     int64_t env_offset = 0;

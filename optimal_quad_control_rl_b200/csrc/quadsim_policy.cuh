@@ -214,6 +214,14 @@ __device__ __forceinline__ void add_exploration_noise(const PolicyParams &P, lon
     a[2] = fmaf(P.std[2], mul_rn(r1, c1), a[2]); a[3] = fmaf(P.std[3], mul_rn(r1, s1), a[3]);
 }
 
+#ifdef QS_EXP_TS_TIMING  // experiment only (profiles/microbench/policy_stages.cu): clock64 stamps of the stages of a chain
+__device__ long long qs_ts_dbg[8192];
+#define QS_TS_STAMP(pt) do { if (blockIdx.x == 0 && (tid & 127) == 0 && it < 16) qs_ts_dbg[(((chain * 2 + half) * 16 + it) * 8 + layer) * 8 + (pt)] = clock64(); } while (0)
+#define QS_SS_STAMP(pt) do { if (blockIdx.x == 0 && tid == 0 && it < 16) qs_ts_dbg[((group * 16 + it) * 8 + layer) * 8 + (pt)] = clock64(); } while (0)
+#else
+#define QS_TS_STAMP(pt) do { } while (0)
+#define QS_SS_STAMP(pt) do { } while (0)
+#endif
 // Persistent, ONE CTA per SM made of `groups` (<= 4) independent tile groups of 128 threads.  The groups share the
 // weights in shared memory; each owns an A-operand buffer (32 KB), 128 accumulator columns of TMEM, an mbarrier and
 // a named block barrier, and walks its own 128-env tiles: thread r of a group owns row r of the tile (its
@@ -260,7 +268,8 @@ __global__ void __launch_bounds__(4 * kPolRows, 1) policy_kernel(const __grid_co
     const bool vec = (P.in_dim & 3) == 0;  // observation rows of 16-byte multiples: float4 loads
     const long long stride = (long long)gridDim.x * groups;
     uint32_t phase = 0;
-    for (long long tile = (long long)blockIdx.x * groups + group; tile < n_tiles; tile += stride) {
+    int it = 0;
+    for (long long tile = (long long)blockIdx.x * groups + group; tile < n_tiles; tile += stride, ++it) {
         const long long env = tile * kPolRows + tid;
         const bool active = env < P.n;
         // ---- A operand of layer 1: this thread's observation row, BF16, K-chunk by K-chunk; column in_dim = 1
@@ -305,17 +314,21 @@ __global__ void __launch_bounds__(4 * kPolRows, 1) policy_kernel(const __grid_co
             const int k = layer == 0 ? P.k1 : kPolHidden;
             // generic-proxy writes of A -> visible to the tensor core's async proxy; TMEM reads of the previous
             // epilogue ordered before the MMAs that overwrite the accumulator
+            QS_SS_STAMP(0);
             fence_proxy_async();
             tc_fence_before();
             group_barrier(group);
+            QS_SS_STAMP(1);
             if (tid == 0) {
                 tc_fence_after();
                 issue_layer(tmem, a_smem, w_smem + w_off, k, last ? kPolOut : kPolHidden, bar_mma);
             }
+            QS_SS_STAMP(2);
             w_off += layer == 0 ? policy_w1_bytes(P.k1) : policy_wh_bytes();
             mbar_wait(bar_mma, phase);
             phase ^= 1u;
             tc_fence_after();
+            QS_SS_STAMP(3);
             if (!last) {
                 // ---- epilogue: ReLU + BF16 in one conversion, straight into the A slabs of the next layer (the MMAs
                 // that read A are done); two 32-column loads in flight
@@ -324,6 +337,7 @@ __global__ void __launch_bounds__(4 * kPolRows, 1) policy_kernel(const __grid_co
                     tmem_ld32(t_lane, v0);
                     tmem_ld32(t_lane + 32u, v1);
                     tmem_ld_wait();
+                    QS_SS_STAMP(4);
                     act_pack_store<4>(v0, s_a + tid * 16, P.activation);
                     act_pack_store<4>(v1, s_a + 4 * kSlab + tid * 16, P.activation);
                     tmem_ld32(t_lane + 64u, v0);
@@ -333,6 +347,7 @@ __global__ void __launch_bounds__(4 * kPolRows, 1) policy_kernel(const __grid_co
                     act_pack_store<4>(v0, s_a + 8 * kSlab + tid * 16, P.activation);
                     if (const_last) act_pack_store<3>(v1, s_a + 12 * kSlab + tid * 16, P.activation);
                     else act_pack_store<4>(v1, s_a + 12 * kSlab + tid * 16, P.activation);
+                    QS_SS_STAMP(5);
                 }
             } else {
                 uint32_t v[8];
@@ -506,7 +521,8 @@ __global__ void __launch_bounds__(kTsChains * kTsThreads, 1) policy_kernel_ts(co
         if (pre && tile < n_tiles) load_obs16(P, tile * kPolRows + row, tile * kPolRows + row < P.n, 16 * half, nx);
     }
     uint32_t phase = 0;
-    for (long long tile = (long long)blockIdx.x * kTsChains + chain; tile < n_tiles; tile += stride) {
+    int it = 0;
+    for (long long tile = (long long)blockIdx.x * kTsChains + chain; tile < n_tiles; tile += stride, ++it) {
         const long long env = tile * kPolRows + row;
         const bool active = env < P.n;
         // ---- A operand of layer 1: the observation row, BF16, two values per TMEM column; thread = (row, 16 columns)
@@ -525,12 +541,15 @@ __global__ void __launch_bounds__(kTsChains * kTsThreads, 1) policy_kernel_ts(co
             const bool last = layer == P.n_hidden;
             const int k = layer == 0 ? P.k1 : kPolHidden;
             // A (tcgen05.st, waited for) and the accumulator reads of the previous epilogue are ordered before the MMAs
+            QS_TS_STAMP(0);
             tc_fence_before();
             chain_barrier(chain);
+            QS_TS_STAMP(1);
             if (tid == 0) {
                 tc_fence_after();
                 issue_layer_ts(t_chain + 64u, t_chain, w_smem + w_off, k, last ? kPolOut : kPolHidden, bar_mma);
             }
+            QS_TS_STAMP(2);
             if (layer == 0 && pre) {  // the loads fly while the chain computes
                 const long long nenv = env + stride * kPolRows;
                 if (tile + stride < n_tiles) load_obs16(P, nenv, nenv < P.n, 16 * half, nx);
@@ -539,12 +558,14 @@ __global__ void __launch_bounds__(kTsChains * kTsThreads, 1) policy_kernel_ts(co
             mbar_wait(bar_mma, phase);
             phase ^= 1u;
             tc_fence_after();
+            QS_TS_STAMP(3);
             if (!last) {
                 // ---- epilogue: accumulator columns [64 half, 64 half + 64) -> activation -> A columns [32 half, 32 half + 32)
                 uint32_t v0[32], v1[32], w[32];
                 tmem_ld32(t_d + 64u * (uint32_t)half, v0);
                 tmem_ld32(t_d + 64u * (uint32_t)half + 32u, v1);
                 tmem_ld_wait();
+                QS_TS_STAMP(4);
                 act_pack16(v0, w, P.activation);
                 act_pack16(v1, w + 16, P.activation);
                 if (half == 1 && const_last) {  // columns 60..63 keep the constant
@@ -555,7 +576,9 @@ __global__ void __launch_bounds__(kTsChains * kTsThreads, 1) policy_kernel_ts(co
                     tmem_st16(t_a + 32u * (uint32_t)half, w);
                     tmem_st16(t_a + 32u * (uint32_t)half + 16u, w + 16);
                 }
+                QS_TS_STAMP(5);
                 tmem_st_wait();
+                QS_TS_STAMP(6);
             } else if (half == 0) {
                 uint32_t v[8];
                 tmem_ld8(t_d, v);

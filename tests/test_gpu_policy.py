@@ -81,6 +81,38 @@ def test_tanh_activation(in_dim, hidden, n_hidden, tracks):
             assert torch.equal(a, c)
 
 
+@pytest.mark.parametrize("in_dim,hidden,n_hidden,act", [(24, 120, 3, "relu"), (17, 120, 3, "relu"), (28, 127, 2, "relu"),
+                                                        (40, 96, 4, "relu"), (24, 120, 3, "tanh"), (20, 64, 1, "tanh")])
+def test_activations_in_tensor_memory_equal_shared_memory_path(in_dim, hidden, n_hidden, act, monkeypatch):
+    """policy_kernel_ts (A operand in TMEM, `tcgen05.mma [d], [a], b-desc`; the default of qs_policy_forward) against
+    policy_kernel (both operands from shared memory): same BF16 operands, same K order, FP32 accumulation in the same
+    tensor core -- the two must agree bit for bit, for every observation width (register-prefetched k1 = 32 and the general
+    path), ragged N, and both activations."""
+    import torch
+    import optimal_quad_control_rl_b200 as Q
+    rng = np.random.default_rng(in_dim * 1000 + hidden)
+    dims = [in_dim] + [hidden] * n_hidden + [4]
+    w = [rng.normal(0, 1 / np.sqrt(dims[l]), (dims[l + 1], dims[l])).astype(np.float32) for l in range(len(dims) - 1)]
+    b = [rng.normal(0, 0.1, dims[l + 1]).astype(np.float32) for l in range(len(dims) - 1)]
+    outs = {}
+    for ts in ("1", "0"):
+        monkeypatch.setenv("QS_POLICY_TS", ts)
+        pol = Q.MlpPolicy(w, b, std=np.full(4, 0.4, np.float32), activation=act, seed=9)
+        for n in (1, 129, 40000):
+            x = torch.from_numpy(rng.normal(0, 1, (n, in_dim)).astype(np.float32) if ts == "1" else outs[("x", n)]).cuda()
+            if ts == "1":
+                outs[("x", n)] = x.cpu().numpy()
+            mean = torch.empty((n, 4), device="cuda")
+            a_det = pol.forward(x, deterministic=True, mean_out=mean).clone()
+            a_smp = pol.forward(x).clone()
+            torch.cuda.synchronize()
+            outs[(ts, n)] = (mean.cpu().numpy(), a_det.cpu().numpy(), a_smp.cpu().numpy())
+    for n in (1, 129, 40000):
+        for got, ref in zip(outs[("1", n)], outs[("0", n)]):
+            np.testing.assert_array_equal(got, ref)
+        assert np.isfinite(outs[("1", n)][0]).all() and np.abs(outs[("1", n)][0]).max() > 1e-3
+
+
 @pytest.mark.parametrize("in_dim,hidden,n_hidden", [(17, 120, 3), (20, 64, 1), (28, 127, 2), (32, 96, 4)])
 def test_other_shapes_random_weights(in_dim, hidden, n_hidden):
     """INDI observation width (17: scalar loads), other gates_ahead, other depths / widths."""

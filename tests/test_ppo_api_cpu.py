@@ -110,3 +110,25 @@ def test_policy_object_has_sb3_layout():
     assert torch.allclose(lp, lp2) and torch.allclose(v, v2) and ent.shape == (7,)
     # SB3's orthogonal init: action net gain 0.01 -> tiny initial means
     assert a.abs().max() < 0.2
+
+
+def test_aliased_infos_behaves_like_the_reference_list():
+    """From 2**16 envs on `step_wait` returns `AliasedInfos` instead of `[info] * N` (the N pointers alone cost ~2 ms per step
+    at N = 2**20): everything SB3 / VecMonitor do with `infos` must give what the reference's aliased list gives."""
+    from optimal_quad_control_rl_b200.envs import AliasedInfos
+    n = 1000
+    info = {"terminal_observation": np.arange(3), "TimeLimit.truncated": True}
+    ref, got = [info] * n, AliasedInfos(info, n)
+    assert len(got) == n and got[0] is info and got[n - 1] is info and got[-1] is info
+    assert all(g is r for g, r in zip(got, ref)) and sum(1 for _ in got) == n
+    assert list(got[:]) == ref and got[10:20] == ref[10:20] and got[::250] == ref[::250] and got == ref
+    with pytest.raises(IndexError):
+        got[n]
+    new_infos = list(got[:])                        # VecMonitor.step_wait: `new_infos = list(infos[:])`
+    new_infos[3] = got[3].copy()
+    new_infos[3]["episode"] = {"r": 1.0}
+    assert "episode" not in info and new_infos[4] is info
+    for idx, done in enumerate([True] * n):         # SB3 collect_rollouts: bootstrap read
+        assert got[idx].get("terminal_observation") is not None and got[idx].get("TimeLimit.truncated", False)
+    got[5]["x"] = 1                                 # writes alias, like the reference's one dict
+    assert got[900]["x"] == 1

@@ -1,7 +1,5 @@
-B="python bench.py --steps 1000 --warmup 100 --no-cpu-baseline --no-configs --e2e-steps 3"
-source <(sed -n '/^line()/,/^}/p' tools/gpu.sh)
-{ for lib in head "" nouni head "" nouni; do
-  QS_LIB=${lib:+build/exp/libquadsim_$lib.so} $B 2>/dev/null | line "e2e ${lib:-product}"
-  QS_LIB=${lib:+build/exp/libquadsim_$lib.so} $B --variant indi 2>/dev/null | line "indi ${lib:-product}"
-done; } 2>&1 | tee gpurun_out/d4_variants.log
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/d4_pytest.log
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/d11_pytest.log
+python tools/bench_numpy_step.py 2>&1 | tee gpurun_out/d11_numpy_step.log
+QS_HOST_THREADS=1 python tools/bench_numpy_step.py 2>&1 | tail -1 | sed 's/^/1 staging thread: /' | tee -a gpurun_out/d11_numpy_step.log
+./build/exp/policy_stages 2>&1 | tee gpurun_out/d11_policy_stages.log | tail -3
+nproc; lscpu | grep -E "Model name|Socket|NUMA node\(s\)" 
