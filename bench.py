@@ -444,6 +444,22 @@ def selfcheck_multi(torch, dist, Q, dev, rank, world):
         e_p2p.step_tensor(a, obs_out=g_p2p.local_slot())
         full_p2p = g_p2p.gather().clone()
         ok_gather &= bool(torch.equal(full_nccl, full_p2p)) and full_p2p.abs().sum().item() > 0
+    # (3) the packed BF16 gather: gathered blocks == round-to-nearest BF16 of the float32 gather, and the policy agrees bit for bit
+    e_pk = make(count, first)
+    g_pk = Q.ObsPeerGather(total, e_pk.state_len, dev, packed=True)
+    g_pk.attach(e_pk)
+    e_pk.reset_tensor(obs_out=g_pk.local_slot())
+    for t in range(8):
+        e_pk.step_tensor(acts[t][first:first + count].contiguous(), obs_out=g_pk.local_slot())
+        full_pk = g_pk.gather()
+    rows = full_pk.view(-1, 4, 32, 8, 2).permute(0, 2, 1, 3, 4).reshape(-1, 32, 2)[:total].contiguous().view(torch.int16).reshape(total, 32)
+    want = torch.zeros((total, 32), device=dev)
+    want[:, :e_pk.state_len] = full_p2p
+    want[:, e_pk.state_len] = 1.0
+    pol = Q.MlpPolicy.from_npz(device=dev)
+    ok_packed = bool(torch.equal(rows, want.to(torch.bfloat16).view(torch.int16))) and \
+        bool(torch.equal(pol.forward_packed(full_pk, total, deterministic=True), pol.forward(full_p2p, deterministic=True)))
+    e_pk.close()
     ok_shard = True
     if rank == 0:
         ref = make(total, 0)
@@ -452,13 +468,13 @@ def selfcheck_multi(torch, dist, Q, dev, rank, world):
             o = ref.step_tensor(acts[t])[0]
         ok_shard = bool(torch.equal(o, full_p2p))
         ref.close()
-    flags = torch.tensor([int(ok_gather), int(ok_shard)], device=dev)
+    flags = torch.tensor([int(ok_gather), int(ok_shard), int(ok_packed)], device=dev)
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     e_nccl.close()
     e_p2p.close()
     res = {"p2p_gather_equals_nccl": bool(flags[0].item()), "sharded_equals_unsharded": bool(flags[1].item()),
-           "envs": total, "steps": 8, "ranks": world}
-    res["status"] = "ok" if all((res["p2p_gather_equals_nccl"], res["sharded_equals_unsharded"])) else "FAILED"
+           "packed_bf16_gather_equals_packed_f32_and_policy_agrees": bool(flags[2].item()), "envs": total, "steps": 8, "ranks": world}
+    res["status"] = "ok" if all(bool(f) for f in flags.tolist()) else "FAILED"
     return res
 
 
@@ -468,17 +484,21 @@ def config4(torch, dist, Q, L, dev, rank, world, local, steps, barrier, peak, to
     first, count = Q.shard_range(total, rank, world)
     bpe = 189 + 4 * (20 + 4 * ga)
     out = []
-    for mode in ("none", "nccl", "p2p"):
+    modes = ("none", "nccl", "p2p") + (("p2p_bf16",) if all(Q.shard_range(total, r, world)[0] % 128 == 0 for r in range(world)) else ())
+    for mode in modes:
         env = make_env(Q, "e2e", count, ga, dev, env_offset=first)
-        env.reset_tensor()
         gen = torch.Generator(device=dev).manual_seed(21 + rank)
         acts = [torch.rand((count, 4), generator=gen, device=dev) * 2 - 1 for _ in range(4)]
         gather = None
         if mode == "nccl":
             gather = Q.ObsAllGather(total, env.state_len, dev)
-        elif mode == "p2p":
-            gather = Q.ObsPeerGather(total, env.state_len, dev)
+        elif mode in ("p2p", "p2p_bf16"):
+            gather = Q.ObsPeerGather(total, env.state_len, dev, packed=mode == "p2p_bf16")
             gather.attach(env)
+        if mode == "p2p_bf16":
+            env.reset_tensor(obs_out=gather.local_slot())
+        else:
+            env.reset_tensor()
 
         def one(i):
             env.step_tensor(acts[i & 3], obs_out=None if gather is None else gather.local_slot())
@@ -496,11 +516,14 @@ def config4(torch, dist, Q, L, dev, rank, world, local, steps, barrier, peak, to
         rec = {"name": "C4_" + mode, "workload": workload_name("e2e", ga, total, f"total_over_{world}gpus"),
                "gather": {"none": "no collective (data-parallel policy)", "nccl": "step kernel writes the send slot; in-place "
                           "ncclAllGather", "p2p": "fused: step kernel bulk-stores its tiles into every peer (symmetric memory), "
-                          "double-buffered, one barrier"}[mode],
+                          "double-buffered, one barrier", "p2p_bf16": "fused, observations packed as BF16 in the on-device "
+                          "policy's operand layout (64 B per env instead of 96; qs_set_obs_format), consumed by "
+                          "qs_policy_forward_packed"}[mode],
                "value": total / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "envs_per_gpu": count,
                "launch": t.launch_mode, "replay_ms_per_step": rep,
                "per_gpu_roofline_frac": count * bpe / (ms * 1e-3) / 1e9 / peak,
-               "nvlink_algorithmic_rx_bytes_per_gpu_per_step": 0 if gather is None else (total - count) * env.state_len * 4}
+               "nvlink_algorithmic_rx_bytes_per_gpu_per_step": 0 if gather is None else
+               (total - count) * (64 if mode == "p2p_bf16" else env.state_len * 4)}
         if nv0 and nv1:
             rec["nvlink_measured_bytes_per_step_rank0"] = {"tx": (nv1[0] - nv0[0]) * 1024 / steps, "rx": (nv1[1] - nv0[1]) * 1024 / steps}
             if gather is not None:

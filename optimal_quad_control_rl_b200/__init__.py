@@ -2,6 +2,7 @@
 behind the reference's own ``Quadcopter3DGates(VecEnv)`` interface."""
 from .tracks import rectangle_track, training_disturbance_ranges, zigzag_track  # noqa: F401
 from .sharding import ObsAllGather, ObsPeerGather, shard_range  # noqa: F401
+from ._lib import QuadsimError  # noqa: F401
 
 
 def __getattr__(name):  # envs needs torch + the CUDA library: import lazily so CPU-only tooling can import the package

@@ -58,6 +58,8 @@ SIGNATURES = {
     "qs_seed": (C.c_int, [_vp, C.c_uint64]),
     "qs_set_env_offset": (C.c_int, [_vp, C.c_int64]),
     "qs_set_obs_peers": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.c_int64]),
+    "qs_set_obs_format": (C.c_int, [_vp, C.c_int]),
+    "qs_obs_packed_bytes": (C.c_int64, [C.c_int64]),
     "qs_enable_stats": (C.c_int, [_vp, C.c_int]),
     "qs_get_stats": (C.c_int, [_vp, C.POINTER(QsStats), C.c_int]),
     "qs_set_state": (C.c_int, [_vp, C.c_int64, C.c_int64, _fp, _fp, _i64p, _i64p]),
@@ -85,6 +87,7 @@ SIGNATURES = {
     "qs_policy_seed": (C.c_int, [_vp, C.c_uint64]),
     "qs_policy_set_env_offset": (C.c_int, [_vp, C.c_int64]),
     "qs_policy_forward": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int]),
+    "qs_policy_forward_packed": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int]),
     "qs_policy_launch_count": (C.c_uint64, [_vp]),
     "qs_rollout": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "qs_rollout_fused_supported": (C.c_int, [_vp, _vp]),

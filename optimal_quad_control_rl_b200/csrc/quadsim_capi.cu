@@ -346,10 +346,24 @@ int qs_set_obs_peers(qs_env *e, int n_peers, void *const *peer_obs_bases, int64_
     // alignment it tests on the LOCAL destination only: the peer rows must be aligned the same way
     if (n_peers && (row_offset < 0 || ((row_offset * e->obs_len * 4) & 15)))
         return fail(e, QS_ERR_ARG, "qs_set_obs_peers: row_offset * obs_len * 4 must be a non-negative multiple of 16");
+    if (n_peers && e->P.obs_packed && (row_offset % qs::kPolRows))
+        return fail(e, QS_ERR_ARG, "qs_set_obs_peers: packed observations need row_offset % 128 == 0");
     e->P.n_peers = n_peers;
     e->P.peer_row_offset = row_offset;
     return QS_OK;
 }
+
+int qs_set_obs_format(qs_env *e, int format) {
+    QS_CHECK_ENV(e);
+    if (format != QS_OBS_F32 && format != QS_OBS_BF16_K32) return fail(e, QS_ERR_ARG, "qs_set_obs_format: unknown format");
+    if (format == QS_OBS_BF16_K32 && e->obs_len > qs::kPackK - 1)
+        return fail(e, QS_ERR_ARG, "qs_set_obs_format: packed observations need obs_len <= 31 (gates_ahead too large)");
+    if (format == QS_OBS_BF16_K32 && e->P.n_peers && (e->P.peer_row_offset % qs::kPolRows))
+        return fail(e, QS_ERR_ARG, "qs_set_obs_format: packed observations need a peer row_offset % 128 == 0");
+    e->P.obs_packed = format == QS_OBS_BF16_K32 ? 1 : 0;
+    return QS_OK;
+}
+int64_t qs_obs_packed_bytes(int64_t n) { return n <= 0 ? 0 : (n + qs::kPolRows - 1) / qs::kPolRows * (4 * (int64_t)qs::kPackBlock); }
 
 int qs_enable_stats(qs_env *e, int on) { QS_CHECK_ENV(e); e->stats_on = on != 0; return QS_OK; }
 
@@ -471,6 +485,7 @@ static int prep_launch(qs_env *e, const char *who) {
 
 static int launch_observe(qs_env *e, float *obs_dev, int reset_all, const char *who) {
     if (!obs_dev) return fail(e, QS_ERR_ARG, "obs_dev is NULL");
+    if (e->P.obs_packed && ((uintptr_t)obs_dev & 15)) return fail(e, QS_ERR_ARG, "a packed obs_dev must be 16-byte aligned");
     if (int r = prep_launch(e, who)) return r;
     e->P.obs = obs_dev;
     if (e->variant == QS_E2E)
@@ -522,6 +537,8 @@ int qs_step(qs_env *e, const float *actions_dev, float *obs_dev, float *rew_dev,
     QS_CHECK_ENV(e);
     if (int r = check_step_args(e, actions_dev, obs_dev, rew_dev, done_dev, mode, reset_source, "qs_step")) return r;
     if ((uintptr_t)actions_dev & 15) return fail(e, QS_ERR_ARG, "qs_step: actions_dev must be 16-byte aligned");
+    if (e->P.obs_packed && ((uintptr_t)obs_dev & 15)) return fail(e, QS_ERR_ARG, "qs_step: a packed obs_dev must be 16-byte aligned");
+    if (e->P.obs_packed && reset_source == QS_RESET_HOST) return fail(e, QS_ERR_STATE, "qs_step: packed observations need the device reset");
     if (int r = prep_launch(e, "qs_step")) return r;
     StepParams &P = e->P;
     P.actions = reinterpret_cast<const float4 *>(actions_dev);
@@ -605,6 +622,7 @@ int qs_step_host_ex(qs_env *e, const void *act, int act_dtype, float *obs, float
     if (int r = check_step_args(e, act, obs, rew, done, mode, reset_source, "qs_step_host")) return r;
     if (act_dtype != QS_F32 && act_dtype != QS_F64) return fail(e, QS_ERR_ARG, "qs_step_host: actions must be float32 or float64");
     if (info && !flags) return fail(e, QS_ERR_ARG, "qs_step_host: info needs the flags buffer");
+    if (e->P.obs_packed) return fail(e, QS_ERR_STATE, "qs_step_host: the env's observation format is packed BF16 (qs_set_obs_format)");
     if (int r = ensure_io(e)) return r;
     if (int r = prep_launch(e, "qs_step_host")) return r;
     StepParams &P = e->P;
@@ -689,6 +707,7 @@ int qs_step_host(qs_env *e, const float *act, float *obs, float *rew, uint8_t *d
 
 static int observe_host(qs_env *e, float *obs, int reset_all) {
     if (!obs) return fail(e, QS_ERR_ARG, "obs_host is NULL");
+    if (e->P.obs_packed) return fail(e, QS_ERR_STATE, "host observations: the env's observation format is packed BF16 (qs_set_obs_format)");
     if (int r = ensure_io(e)) return r;
     if (int r = launch_observe(e, e->h_obs, reset_all, reset_all ? "qs_reset_all_host" : "qs_observe_host")) return r;
     QS_CUDA(e, cudaMemcpyAsync(obs, e->h_obs, (size_t)e->n * e->obs_len * 4, cudaMemcpyDeviceToHost, e->stream));
@@ -882,25 +901,27 @@ static int policy_params(qs_policy *p, int64_t n, int deterministic, cudaStream_
 }
 
 static int policy_launch(qs_policy *p, const float *obs_dev, int64_t n, float *actions_dev, float *mean_dev, float *raw_dev,
-                         int deterministic, cudaStream_t stream) {
+                         int deterministic, cudaStream_t stream, bool packed = false) {
     qs::PolicyParams P{};
     if (int r = policy_params(p, n, deterministic, stream, P)) return r;
     P.obs = obs_dev; P.actions = actions_dev; P.mean = mean_dev; P.raw = raw_dev;
+    P.obs_packed = packed ? 1 : 0;
+    const bool ts = p->ts && !packed;  // (the TMEM-activation kernel reads float32 rows only)
     const long long tiles = (n + qs::kPolRows - 1) / qs::kPolRows;
     void *args[] = {&P};
     cudaLaunchConfig_t cfg{};
-    const int per_cta = p->ts ? qs::kTsChains : p->groups;  // 128-row tiles in flight per CTA
+    const int per_cta = ts ? qs::kTsChains : p->groups;  // 128-row tiles in flight per CTA
     const long long ctas = (tiles + per_cta - 1) / per_cta;
     cfg.gridDim = dim3((unsigned)(ctas < p->grid ? ctas : p->grid));
-    cfg.blockDim = dim3((unsigned)(p->ts ? qs::kTsChains * qs::kTsThreads : qs::kPolRows * p->groups));
-    cfg.dynamicSmemBytes = p->ts ? qs::policy_ts_smem_bytes(p->k1, p->n_hidden) : p->smem;
+    cfg.blockDim = dim3((unsigned)(ts ? qs::kTsChains * qs::kTsThreads : qs::kPolRows * p->groups));
+    cfg.dynamicSmemBytes = ts ? qs::policy_ts_smem_bytes(p->k1, p->n_hidden) : p->smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = p->pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t c = cudaLaunchKernelExC(&cfg, p->ts ? (const void *)qs::policy_kernel_ts : (const void *)qs::policy_kernel, args);
+    cudaError_t c = cudaLaunchKernelExC(&cfg, ts ? (const void *)qs::policy_kernel_ts : (const void *)qs::policy_kernel, args);
     if (c != cudaSuccess) { p->err = std::string("policy_kernel launch: ") + cudaGetErrorString(c); return QS_ERR_CUDA; }
     p->launches++;
     return QS_OK;
@@ -916,6 +937,16 @@ int qs_policy_forward(qs_policy *p, const float *obs_dev, int64_t n, float *acti
     return policy_launch(p, obs_dev, n, actions_dev, mean_dev, raw_dev, deterministic, p->stream);
 }
 
+int qs_policy_forward_packed(qs_policy *p, const void *packed_obs_dev, int64_t n, float *actions_dev, float *mean_dev,
+                             float *raw_dev, int deterministic) {
+    QS_PCHECK(p);
+    if (!packed_obs_dev || !actions_dev || n <= 0) return pfail(p, QS_ERR_ARG, "qs_policy_forward_packed: bad argument");
+    if (p->k1 > qs::kPackK) return pfail(p, QS_ERR_ARG, "qs_policy_forward_packed: packed observations need in_dim <= 31");
+    if (((uintptr_t)packed_obs_dev & 15) || ((uintptr_t)actions_dev & 15) || ((uintptr_t)mean_dev & 15) || ((uintptr_t)raw_dev & 15))
+        return pfail(p, QS_ERR_ARG, "qs_policy_forward_packed: buffers must be 16-byte aligned");
+    return policy_launch(p, (const float *)packed_obs_dev, n, actions_dev, mean_dev, raw_dev, deterministic, p->stream, true);
+}
+
 // collect_rollouts on the device (SB3 `OnPolicyAlgorithm.collect_rollouts`, called from `3D quad race.ipynb:820`): for
 // t < steps:  actions[t] = policy(obs[t]);  obs[t+1], rewards[t], dones[t] = env.step(actions[t]).  2*steps kernel
 // launches enqueued back to back on the env's stream (PDL-chained), no host round trip.  obs[0] must hold the
@@ -926,6 +957,7 @@ int qs_rollout(qs_env *e, qs_policy *p, int steps, float *obs_buf, float *act_bu
     if (!p) return fail(e, QS_ERR_ARG, "qs_rollout: policy is NULL");
     if (steps < 1 || !obs_buf || !act_buf || !rew_buf || !done_buf) return fail(e, QS_ERR_ARG, "qs_rollout: bad argument");
     if (p->in_dim != e->obs_len) return fail(e, QS_ERR_ARG, "qs_rollout: policy input width != observation width");
+    if (e->P.obs_packed) return fail(e, QS_ERR_STATE, "qs_rollout: the rollout buffers hold float32 rows; the env's observation format is packed BF16");
     if (p->out_dim != 4) return fail(e, QS_ERR_ARG, "qs_rollout: the env takes 4 actions");
     if (p->device != e->device) return fail(e, QS_ERR_ARG, "qs_rollout: env and policy live on different devices");
     const size_t n = (size_t)e->n;
@@ -957,6 +989,7 @@ int qs_rollout_fused(qs_env *e, qs_policy *p, int steps, float *obs_buf, float *
     if (!p) return fail(e, QS_ERR_ARG, "qs_rollout_fused: policy is NULL");
     if (steps < 1 || !obs_buf || !act_buf || !rew_buf || !done_buf) return fail(e, QS_ERR_ARG, "qs_rollout_fused: bad argument");
     if (((uintptr_t)act_buf & 15) || ((uintptr_t)raw_buf & 15)) return fail(e, QS_ERR_ARG, "qs_rollout_fused: action buffers must be 16-byte aligned");
+    if (e->P.obs_packed) return fail(e, QS_ERR_STATE, "qs_rollout_fused: the rollout buffers hold float32 rows; the env's observation format is packed BF16");
     if (!qs_rollout_fused_supported(e, p))
         return fail(e, QS_ERR_ARG, "qs_rollout_fused: this env / policy shape does not fit the fused kernel (use qs_rollout)");
     if (int r = prep_launch(e, "qs_rollout_fused")) return r;

@@ -84,6 +84,9 @@ struct StepParams {
     // arrivals) advances it, i.e. after every CTA of this launch has read it and before the next launch may.
     unsigned long long *epoch;
     int n_gates, gates_ahead, obs_len;
+    // 0: observations leave as float32 rows (N, obs_len), the reference's layout.  1: as BF16 in the on-device policy's
+    // A-operand layout (pack_obs_row / kPackBlock below) -- `obs` and `peer_obs` then point to packed buffers
+    int obs_packed;
     int mode, reset_source;
     int l2_hints;  // 1: state evict_last, streams evict_first (see l2_policy_*); 0: no cache hints
     long long keep_blocks;  // with l2_hints: only the first keep_blocks 32-env state blocks are pinned (what fits in L2)
@@ -363,6 +366,39 @@ __device__ __forceinline__ void store_obs_tile(float *dst, const float *s_obs, i
         __syncthreads();
         for (int i = threadIdx.x; i < rows * obs_len; i += kBlock) dst[i] = s_obs[i];
     }
+}
+
+// ---- packed observations: what the step hands to the on-device policy when nobody needs float32 rows (a sharded job
+// whose policy reads the all-gathered observations, BASELINE.json config 4).  One 2 KB block per 32 envs:
+//   [K chunk c = 0..3][row r = 0..31][8 x BF16]      = the policy kernel's K-major A-operand slabs for its first layer
+// (K = 32 columns: obs_len <= 31 values, the constant 1 that multiplies the folded bias at column obs_len, zeros
+// after it), 64 B per env instead of 96 / 68 B of float32 -- a third less to move through NVLink, and the policy loads
+// it with TMA straight into the MMA's operand buffer (no load / convert / store instructions at all).
+constexpr int kPackK = 32;
+constexpr int kPackBlock = (kPackK / 8) * 32 * 16;  // 2048 B per 32 envs
+__device__ __forceinline__ uint32_t pack_bf16_rn(float lo, float hi) {  // round-to-nearest-even, lo in the low half
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// this thread's float32 row (in shared memory) -> 16 BF16 pairs; inactive rows pack to zero
+__device__ __forceinline__ void pack_obs_row(const float *row, int obs_len, bool active, uint32_t (&w)[16]) {
+    float x[kPackK];
+    if ((obs_len & 3) == 0) {
+#pragma unroll
+        for (int q = 0; q < kPackK / 4; ++q) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * q < obs_len) v = *reinterpret_cast<const float4 *>(row + 4 * q);
+            x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kPackK; ++k) x[k] = k < obs_len ? row[k] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < kPackK; ++k) x[k] = active ? (k == obs_len ? 1.0f : x[k]) : 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) w[c] = pack_bf16_rn(x[2 * c], x[2 * c + 1]);
 }
 
 __device__ __forceinline__ void load_track(const StepParams &P, float *s_track) {
@@ -695,9 +731,11 @@ template <int V> struct Stage : Blk<V> {
 constexpr int kBarBytes = 128;  // mbarriers live in the first 128 bytes of dynamic shared memory
 constexpr int kWarps = kBlock / 32;
 
+// a warp's observation staging slice: its 32 float32 rows, and never less than one packed BF16 block (kPackBlock)
+__host__ __device__ constexpr int step_slice_floats(int obs_len) { return 32 * obs_len > 512 ? 32 * obs_len : 512; }
 __host__ __device__ constexpr size_t step_smem_bytes(int variant, int stages, int obs_len, int n_gates) {
     return kBarBytes + (size_t)stages * kWarps * (variant == kE2E ? (int)Stage<kE2E>::BYTES : (int)Stage<kINDI>::BYTES) +
-           (size_t)kBlock * obs_len * 4 + (size_t)n_gates * kTrackRow * 4;
+           (size_t)kWarps * step_slice_floats(obs_len) * 4 + (size_t)n_gates * kTrackRow * 4;
 }
 
 // lane 0 of a warp: fill one of the warp's stages with the 32 envs starting at `first`
@@ -740,7 +778,8 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw) + warp * kStages;          // this warp's barriers
     unsigned char *stages = smem_raw + kBarBytes + warp * (kStages * S::BYTES);          // this warp's ring
     float *s_obs = reinterpret_cast<float *>(smem_raw + kBarBytes + kWarps * kStages * S::BYTES);
-    float *s_track = s_obs + kBlock * P.obs_len;
+    const int slice = step_slice_floats(P.obs_len);
+    float *s_track = s_obs + kWarps * slice;
     const long long n_tiles = P.tile_end;
     const long long tile0 = P.tile_begin + blockIdx.x;
 
@@ -769,8 +808,8 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
     unsigned c_act = 0, c_done = 0, c_tr = 0, c_gp = 0, c_gc = 0, c_gr = 0, c_ob = 0;
     const bool write_obs_tile = P.mode != kModePause;
     const bool fused_reset = P.mode == kModeNormal && P.reset_source == kResetDevice;
-    float *const my_obs = s_obs + tid * P.obs_len;
-    float *const warp_obs = s_obs + warp * 32 * P.obs_len;
+    float *const warp_obs = s_obs + warp * slice;
+    float *const my_obs = warp_obs + lane * P.obs_len;
     bool obs_in_flight = false;  // warp-uniform: a bulk store of this warp's observation slice may still be reading it
     int it = 0;
     for (long long tile = tile0; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -894,6 +933,33 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
 #else
             write_obs<V>(P, s_track, n, tg, my_obs);
 #endif
+            if (P.obs_packed) {  // warp-uniform: the rows leave as ONE packed 2 KB block (see pack_obs_row)
+                uint32_t w[16];
+                pack_obs_row(my_obs, P.obs_len, active, w);
+                __syncwarp();  // every lane has read its float32 row: the block is built over them
+                uint4 *blk = reinterpret_cast<uint4 *>(warp_obs);
+#pragma unroll
+                for (int c = 0; c < kPackK / 8; ++c) blk[c * 32 + lane] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    const long long b32 = tile * kWarps + warp;  // 32-env block index within this launch's env range
+                    unsigned char *pk = reinterpret_cast<unsigned char *>(P.obs) + b32 * (long long)kPackBlock;
+                    if (kHints) bulk_store_hint(pk, warp_obs, kPackBlock, pol_stream);
+                    else bulk_store(pk, warp_obs, kPackBlock);
+#pragma unroll 1
+                    for (int p = 0; p < P.n_peers; ++p)
+                        bulk_store(reinterpret_cast<unsigned char *>(P.peer_obs[p]) + ((P.peer_row_offset >> 5) + b32) * (long long)kPackBlock,
+                                   warp_obs, kPackBlock);
+                }
+                obs_in_flight = true;
+                if (P.stats && active) {
+                    reward_acc += reward;
+                    c_act += 1; c_done += (fl & F_DONE) != 0; c_tr += (fl & F_TRUNC) != 0; c_gp += (fl & F_PASSED) != 0;
+                    c_gc += (fl & F_COLLISION) != 0; c_gr += (fl & F_GROUND) != 0; c_ob += (fl & F_OOB) != 0;
+                }
+                continue;
+            }
             const long long rem = P.n - (base + warp * 32);
             const int rows = rem < 32 ? (rem < 0 ? 0 : (int)rem) : 32;
             float *dst = P.obs + (base + warp * 32) * P.obs_len;
@@ -996,6 +1062,15 @@ __global__ void __launch_bounds__(kBlock) observe_kernel(const __grid_constant__
             tg = field<V, Blk<V>::META, uint32_t>(P.s, env) >> 24;
         }
         write_obs<V>(P, s_track, e, tg, s_obs + threadIdx.x * P.obs_len);
+    }
+    if (P.obs_packed) {  // packed blocks: four coalesced 512-byte stores per warp, straight from registers
+        uint32_t w[16];
+        pack_obs_row(s_obs + threadIdx.x * P.obs_len, P.obs_len, env < P.n, w);
+        uint4 *blk = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(P.obs) + (env >> 5) * (long long)kPackBlock);
+#pragma unroll
+        for (int c = 0; c < kPackK / 8; ++c) blk[c * 32 + (threadIdx.x & 31)] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+        if (reset_all && threadIdx.x == 0) epoch_arrive(P);
+        return;
     }
     const long long rem = P.n - base;
     store_obs_tile(P.obs + base * P.obs_len, s_obs, rem < kBlock ? (int)rem : kBlock, P.obs_len);  // block barrier inside

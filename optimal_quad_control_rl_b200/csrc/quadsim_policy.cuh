@@ -34,7 +34,8 @@ constexpr int kPolOnes = kPolHidden - 1;  // hidden unit that carries the consta
 constexpr int kSlab = kPolRows * 16;      // one K-chunk of 8 BF16 for 128 rows: 2 KB
 
 struct PolicyParams {
-    const float *obs;         // (n, in_dim) f32 row-major
+    const float *obs;         // (n, in_dim) f32 row-major; with obs_packed: the step kernel's packed BF16 blocks (kPackBlock)
+    int obs_packed;           // 1: `obs` already holds the first layer's A operand (k1 <= kPackK): TMA-loaded, nothing converted
     float *actions;           // (n, 4) f32: clip(mean + std * N(0,1), -1, 1)
     float *mean;              // (n, 4) f32 network output before noise, or NULL
     float *raw;               // (n, 4) f32 sampled action BEFORE the clip (what PPO's log-prob is taken of), or NULL
@@ -238,11 +239,12 @@ __global__ void __launch_bounds__(4 * kPolRows, 1) policy_kernel(const __grid_co
     unsigned char *s_a = smem_raw + 128 + group * ((kPolHidden / 8) * kSlab);
     unsigned char *s_w = smem_raw + 128 + groups * ((kPolHidden / 8) * kSlab);
     uint64_t *bar_mma = bar_mma_all + group;
+    uint64_t *bar_obs = reinterpret_cast<uint64_t *>(smem_raw + 72) + group;  // packed observations of a tile landed
     const long long n_tiles = (P.n + kPolRows - 1) / kPolRows;
 
     if (threadIdx.x == 0) {
         mbar_init(bar_w, 1);
-        for (int g = 0; g < groups; ++g) mbar_init(bar_mma_all + g, 1);
+        for (int g = 0; g < groups; ++g) { mbar_init(bar_mma_all + g, 1); mbar_init(reinterpret_cast<uint64_t *>(smem_raw + 72) + g, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(bar_w, P.weight_bytes);
         bulk_load(s_w, P.weights, P.weight_bytes, bar_w);  // launch constant: may precede the PDL wait
@@ -267,13 +269,25 @@ __global__ void __launch_bounds__(4 * kPolRows, 1) policy_kernel(const __grid_co
     const unsigned long long epoch = P.deterministic ? 0ull : *reinterpret_cast<const volatile unsigned long long *>(P.epoch);
     const bool vec = (P.in_dim & 3) == 0;  // observation rows of 16-byte multiples: float4 loads
     const long long stride = (long long)gridDim.x * groups;
-    uint32_t phase = 0;
+    uint32_t phase = 0, obs_phase = 0;
     int it = 0;
     for (long long tile = (long long)blockIdx.x * groups + group; tile < n_tiles; tile += stride, ++it) {
         const long long env = tile * kPolRows + tid;
         const bool active = env < P.n;
-        // ---- A operand of layer 1: this thread's observation row, BF16, K-chunk by K-chunk; column in_dim = 1
-        {
+        // ---- A operand of layer 1.  Packed observations (the step kernel's BF16 blocks, one per 32 rows) ARE the operand:
+        // sixteen 512-byte TMA copies put the tile's four K-chunk slabs in place; nobody loads, converts or stores a value.
+        if (P.obs_packed) {
+            if (tid == 0) {
+                mbar_expect_tx(bar_obs, (uint32_t)(P.k1 / 8) * kSlab);  // k1 <= kPackK: a narrow first layer reads the first chunks only
+                const unsigned char *src = reinterpret_cast<const unsigned char *>(P.obs) + tile * (long long)(4 * kPackBlock);
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    for (int c = 0; c < P.k1 / 8; ++c)
+                        bulk_load(s_a + c * kSlab + b * 512, src + b * kPackBlock + c * 512, 512u, bar_obs);
+            }
+            mbar_wait(bar_obs, obs_phase);
+            obs_phase ^= 1u;
+        } else {
             const float *row = P.obs + env * P.in_dim;
             for (int c = 0; c < P.k1 / 8; ++c) {
                 float x[8];
@@ -300,7 +314,7 @@ __global__ void __launch_bounds__(4 * kPolRows, 1) policy_kernel(const __grid_co
                     make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
             }
         }
-        {  // the next tile's observation rows: start them towards L2 now, a whole tile of compute before they are read
+        if (!P.obs_packed) {  // the next tile's observation rows: start them towards L2 now, a whole tile of compute before they are read
             const long long nenv = env + stride * kPolRows;
             if (nenv < P.n) {
                 const float *nrow = P.obs + nenv * P.in_dim;

@@ -117,6 +117,7 @@ class _QuadGatesBase(_VecEnvBase):
         if self.device.index is None:  # "cuda" = the CURRENT device, not ordinal 0
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.reset_rng = reset_rng
+        self._obs_format = "f32"
         self.lazy_infos_from = 1 << 16  # step_wait returns AliasedInfos instead of a list of N references from this size on
 
         # -- race track (`:298-302`)
@@ -372,6 +373,8 @@ class _QuadGatesBase(_VecEnvBase):
     def current_obs_tensor(self):
         """The observations of the current state as a CUDA tensor (N, D): what ``step_tensor`` / ``rollout`` last wrote,
         recomputed from the state if NumPy-path steps ran in between."""
+        if self._obs_format != "f32":
+            raise L.QuadsimError("current_obs_tensor: the env's observation format is packed BF16; set obs_format = 'f32' first")
         if self._ring_stale:
             self._push_config()
             self._sync_stream()
@@ -431,14 +434,28 @@ class _QuadGatesBase(_VecEnvBase):
         return self.states, rewards, dones, self._infos(info)
 
     # ------------------------------------------------------------------------------------------ tensor fast path
-    def reset_tensor(self):
-        """reset() with the fused device RNG; returns the observation tensor (N,D) on the GPU."""
+    def reset_tensor(self, obs_out=None):
+        """reset() with the fused device RNG; returns the observation tensor (N,D) on the GPU (or fills ``obs_out``)."""
         self._push_config()
         self._sync_stream()
+        if obs_out is not None or self._obs_format != "f32":
+            self._check_obs_out(obs_out)
+            self._call("qs_reset_all", L._vp(obs_out.data_ptr()))
+            self._ring_stale = True
+            return obs_out
         k = self._next_slot()
         self._call("qs_reset_all", L._vp(self._obs_ring[k].data_ptr()))
         self._ring_stale = False
         return self._obs_ring[k]
+
+    def _check_obs_out(self, obs_out):
+        if self._obs_format == "f32":
+            if obs_out.dtype != torch.float32 or not obs_out.is_cuda or not obs_out.is_contiguous() \
+                    or obs_out.numel() < self.num_envs * self.state_len:
+                raise ValueError("obs_out must be a contiguous float32 CUDA tensor of (num_envs, obs_len)")
+        elif obs_out is None or obs_out.dtype != torch.uint8 or not obs_out.is_cuda or not obs_out.is_contiguous() \
+                or obs_out.numel() < self.packed_obs_bytes():
+            raise ValueError(f"obs_format 'bf16_k32': obs_out must be a contiguous uint8 CUDA tensor of >= {self.packed_obs_bytes()} bytes")
 
     def step_tensor(self, actions, obs_out=None):
         """Zero-copy step: ``actions`` is a float32 CUDA tensor (N,4); returns (obs, reward, done, flags) CUDA
@@ -448,6 +465,8 @@ class _QuadGatesBase(_VecEnvBase):
             raise ValueError("step_tensor needs a contiguous float32 CUDA tensor of shape (num_envs, 4)")
         self._push_config()
         self._sync_stream()
+        if obs_out is not None or self._obs_format != "f32":
+            self._check_obs_out(obs_out)
         k = self._next_slot()
         obs_d = self._obs_ring[k] if obs_out is None else obs_out
         self._call("qs_step", L._vp(actions.data_ptr()), L._vp(obs_d.data_ptr()),
@@ -491,6 +510,25 @@ class _QuadGatesBase(_VecEnvBase):
         (device pointers of peer memory) at row ``row_offset + env``.  ``peer_ptrs=[]`` switches it off."""
         arr = (L._vp * max(1, len(peer_ptrs)))(*[L._vp(int(p)) for p in peer_ptrs])
         self._call("qs_set_obs_peers", len(peer_ptrs), arr, int(row_offset))
+
+    # ---- observation format of the tensor path (`step_tensor` / `reset_tensor` with ``obs_out=``)
+    @property
+    def obs_format(self):
+        return self._obs_format
+
+    @obs_format.setter
+    def obs_format(self, fmt):
+        """``"f32"``: float32 rows (N, D), the reference's layout.  ``"bf16_k32"``: packed BF16 blocks in the on-device policy's
+        operand layout (`qs_set_obs_format`; 64 B per env) for a sharded job whose gathered observations only feed
+        ``MlpPolicy.forward_packed``.  In that format ``step_tensor`` / ``reset_tensor`` need ``obs_out=`` (a uint8 CUDA
+        tensor of ``packed_obs_bytes()`` bytes) and the NumPy-facing ``step`` / ``reset`` / ``rollout`` are unavailable."""
+        if fmt not in ("f32", "bf16_k32"):
+            raise ValueError("obs_format must be 'f32' or 'bf16_k32'")
+        self._call("qs_set_obs_format", 1 if fmt == "bf16_k32" else 0)
+        self._obs_format = fmt
+
+    def packed_obs_bytes(self, n=None):
+        return int(self._lib.qs_obs_packed_bytes(int(self.num_envs if n is None else n)))
 
     def enable_stats(self, on=True):
         self._call("qs_enable_stats", int(on))

@@ -116,6 +116,24 @@ class MlpPolicy:
                    L._vp(raw_out.data_ptr()) if raw_out is not None else None, int(bool(deterministic)))
         return out
 
+    def forward_packed(self, packed_obs, n, deterministic=False, out=None, mean_out=None, raw_out=None):
+        """The same forward over the step kernel's packed BF16 observation blocks (``env.obs_format = "bf16_k32"``: a uint8
+        CUDA tensor of ``env.packed_obs_bytes(n)`` bytes, e.g. what ``ObsPeerGather(packed=True).gather()`` returns): the
+        blocks are the first MMA's operand as they are (TMA-loaded; nothing is converted).  Bit-identical to ``forward``
+        on the float32 rows."""
+        if packed_obs.dtype != torch.uint8 or not packed_obs.is_cuda or not packed_obs.is_contiguous():
+            raise ValueError("forward_packed needs a contiguous uint8 CUDA tensor (packed BF16 observation blocks)")
+        need = self._lib.qs_obs_packed_bytes(int(n))
+        if packed_obs.numel() < need:
+            raise ValueError(f"packed observations of {n} envs take {need} bytes, got {packed_obs.numel()}")
+        if out is None:
+            out = torch.empty((n, 4), dtype=torch.float32, device=packed_obs.device)
+        self._call("qs_policy_set_stream", L._vp(torch.cuda.current_stream(self.device).cuda_stream))
+        self._call("qs_policy_forward_packed", L._vp(packed_obs.data_ptr()), int(n), L._vp(out.data_ptr()),
+                   L._vp(mean_out.data_ptr()) if mean_out is not None else None,
+                   L._vp(raw_out.data_ptr()) if raw_out is not None else None, int(bool(deterministic)))
+        return out
+
     def set_weights(self, weights, biases, std=None):
         """Replace the parameters (after a PPO update); shapes must not change."""
         for l, (w, b) in enumerate(zip(weights, biases)):

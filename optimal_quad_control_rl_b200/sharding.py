@@ -60,18 +60,32 @@ class ObsPeerGather:
     barrier t, consumers of t, step t+1, barrier t+1, ...).  So nobody overwrites a buffer a peer still reads, as long
     as the consumers run on the stream ``gather()`` was called on."""
 
-    def __init__(self, total_envs, obs_len, device, group=None):
+    PACK_TILE, PACK_TILE_BYTES = 128, 8192  # packed format: 4 blocks of 32 envs x 2 KB per 128-env policy tile
+
+    def __init__(self, total_envs, obs_len, device, group=None, packed=False):
+        """``packed=True``: the buffers hold the step kernel's packed BF16 blocks (``env.obs_format = "bf16_k32"``,
+        64 B per env over NVLink instead of ``4 * obs_len``) for ``MlpPolicy.forward_packed``; every rank's slice must
+        then start on a multiple of 128 envs."""
         import torch.distributed._symmetric_memory as symm_mem
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         self.first, self.count = shard_range(total_envs, self.rank, self.world)
-        if (self.first * obs_len * 4) % 16:
+        self.packed = bool(packed)
+        self.total_envs = int(total_envs)
+        if self.packed:
+            if any(shard_range(total_envs, r, self.world)[0] % self.PACK_TILE for r in range(self.world)):
+                raise ValueError("ObsPeerGather(packed=True): every rank's slice must start on a multiple of 128 envs")
+        elif (self.first * obs_len * 4) % 16:
             raise ValueError("ObsPeerGather: this rank's slice must start on a 16-byte boundary "
                              "(first_env * obs_len * 4 % 16 == 0) for the TMA bulk stores into peer memory")
         self.bufs, self.handles, self.peer_ptrs = [], [], []
         for _ in range(2):
-            b = symm_mem.empty((total_envs, obs_len), dtype=torch.float32, device=device)
+            if self.packed:
+                tiles = (int(total_envs) + self.PACK_TILE - 1) // self.PACK_TILE
+                b = symm_mem.empty((tiles * self.PACK_TILE_BYTES,), dtype=torch.uint8, device=device)
+            else:
+                b = symm_mem.empty((total_envs, obs_len), dtype=torch.float32, device=device)
             b.zero_()
             h = symm_mem.rendezvous(b, self.group)
             self.bufs.append(b)
@@ -88,10 +102,16 @@ class ObsPeerGather:
     def attach(self, env):
         """Point ``env``'s step kernel at the peers; its ``obs_out`` must be ``local_slot()``."""
         self.env = env
+        if self.packed and env.obs_format != "bf16_k32":
+            env.obs_format = "bf16_k32"
         env.set_obs_peers(self.peer_ptrs[self.parity], self.first)
 
     def local_slot(self):
         """Where this rank's NEXT step must write its observations (``step_tensor(..., obs_out=local_slot())``)."""
+        if self.packed:
+            lo = self.first // self.PACK_TILE * self.PACK_TILE_BYTES
+            hi = lo + (self.count + self.PACK_TILE - 1) // self.PACK_TILE * self.PACK_TILE_BYTES
+            return self.bufs[self.parity][lo:hi]
         return self.bufs[self.parity][self.first:self.first + self.count]
 
     def gather(self):

@@ -42,6 +42,27 @@ for t in range(8):
     full_p2p = g_p2p.gather().clone()
     assert torch.equal(full_nccl, full_p2p), (rank, t)
     assert full_p2p.abs().sum().item() > 0                 # no extra barrier: ObsPeerGather double-buffers
+# the packed BF16 gather (64 B per env over NVLink): same envs, the gathered buffer is the policy's operand as it is
+e_pk = make()
+g_pk = Q.ObsPeerGather(total, e_pk.state_len, dev, packed=True)
+g_pk.attach(e_pk)
+e_pk.reset_tensor(obs_out=g_pk.local_slot())
+pol = Q.MlpPolicy.reference_controller(device=dev)
+for t in range(8):
+    a = acts[t][first:first + count].contiguous()
+    e_pk.step_tensor(a, obs_out=g_pk.local_slot())
+    full_pk = g_pk.gather()
+    blocks = full_pk.view(-1, 4, 32, 8, 2)                                         # [32-env block][chunk][row][8 x bf16 as 2 bytes]
+    rows = blocks.permute(0, 2, 1, 3, 4).reshape(-1, 32, 2)[:total].contiguous().view(torch.int16).reshape(total, 32)
+torch.cuda.synchronize()
+# (the float32 reference of the LAST step: full_p2p, gathered above from identically seeded envs)
+want = torch.zeros((total, 32), device=dev)
+want[:, :e_pk.state_len] = full_p2p
+want[:, e_pk.state_len] = 1.0
+assert torch.equal(rows, want.to(torch.bfloat16).view(torch.int16)), "packed gather != pack(float32 gather)"
+a_pk = pol.forward_packed(full_pk, total, deterministic=True)
+a_f32 = pol.forward(full_p2p, deterministic=True)
+assert torch.equal(a_pk, a_f32), "policy on the packed gather != policy on the float32 gather"
 # sharding is invisible: rank 0 also runs the unsharded env and compares the last gathered observations
 if rank == 0:
     ref = Q.Quadcopter3DGates(total, gp, gy, sp, gates_ahead=1, device=dev, reset_rng="device", seed=4)
