@@ -219,9 +219,11 @@ __device__ __forceinline__ void add_exploration_noise(const PolicyParams &P, lon
 __device__ long long qs_ts_dbg[8192];
 #define QS_TS_STAMP(pt) do { if (blockIdx.x == 0 && (tid & 127) == 0 && it < 16) qs_ts_dbg[(((chain * 2 + half) * 16 + it) * 8 + layer) * 8 + (pt)] = clock64(); } while (0)
 #define QS_SS_STAMP(pt) do { if (blockIdx.x == 0 && tid == 0 && it < 16) qs_ts_dbg[((group * 16 + it) * 8 + layer) * 8 + (pt)] = clock64(); } while (0)
+#define QS_SS_STAMP_AT(it_, layer_, pt) do { if (blockIdx.x == 0 && tid == 0 && (it_) >= 0 && (it_) < 16) qs_ts_dbg[((group * 16 + (it_)) * 8 + (layer_)) * 8 + (pt)] = clock64(); } while (0)
 #else
 #define QS_TS_STAMP(pt) do { } while (0)
 #define QS_SS_STAMP(pt) do { } while (0)
+#define QS_SS_STAMP_AT(it_, layer_, pt) do { } while (0)
 #endif
 // Persistent, ONE CTA per SM made of `groups` (<= 4) independent tile groups of 128 threads.  The groups share the
 // weights in shared memory; each owns an A-operand buffer (32 KB), 128 accumulator columns of TMEM, an mbarrier and
@@ -314,6 +316,7 @@ __global__ void __launch_bounds__(4 * kPolRows, 1) policy_kernel(const __grid_co
                     make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
             }
         }
+        QS_SS_STAMP_AT(it - 1, P.n_hidden, 6);  // the previous tile's last stage: this tile's A operand is in shared memory
         if (!P.obs_packed) {  // the next tile's observation rows: start them towards L2 now, a whole tile of compute before they are read
             const long long nenv = env + stride * kPolRows;
             if (nenv < P.n) {
@@ -367,6 +370,7 @@ __global__ void __launch_bounds__(4 * kPolRows, 1) policy_kernel(const __grid_co
                 uint32_t v[8];
                 tmem_ld8(t_lane, v);
                 tmem_ld_wait();
+                QS_SS_STAMP(4);
                 float a[4] = {__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])};
                 if (active) {
                     if (P.mean) *reinterpret_cast<float4 *>(P.mean + env * 4) = make_float4(a[0], a[1], a[2], a[3]);
@@ -376,6 +380,7 @@ __global__ void __launch_bounds__(4 * kPolRows, 1) policy_kernel(const __grid_co
                     for (int k2 = 0; k2 < 4; ++k2) a[k2] = fminf(fmaxf(a[k2], -1.0f), 1.0f);  // `nn_controller.c:171-173`
                     *reinterpret_cast<float4 *>(P.actions + env * 4) = make_float4(a[0], a[1], a[2], a[3]);
                 }
+                QS_SS_STAMP(5);
             }
         }
     }

@@ -72,10 +72,15 @@ int main() {
             for (int layer = 0; layer <= n_hidden; ++layer) {
                 double s[6] = {0};
                 for (int it = 2; it < 12; ++it) {
-                    for (int pt = 0; pt < (layer == n_hidden ? 3 : 5); ++pt) s[pt] += (double)(ss(g, it, layer, pt + 1) - ss(g, it, layer, pt)) / 10;
+                    for (int pt = 0; pt < 5; ++pt) s[pt] += (double)(ss(g, it, layer, pt + 1) - ss(g, it, layer, pt)) / 10;
                     const long long next0 = layer < n_hidden ? ss(g, it, layer + 1, 0) : ss(g, it + 1, 0, 0);
                     s[5] += (double)(next0 - ss(g, it, layer, 0)) / 10;
                 }
+                if (layer == n_hidden) {  // last layer: 3>4 = accumulator read (+ next tile's loads issued), 4>5 = action epilogue, 5>6 = next tile's A operand stored
+                    double t6 = 0;
+                    for (int it = 2; it < 12; ++it) t6 += (double)(ss(g, it, layer, 6) - ss(g, it, layer, 5)) / 10;
+                    printf("  %d      %8.0f %8.0f %8.0f %8.0f %8.0f  next-A %6.0f | %6.0f\n", layer, s[0], s[1], s[2], s[3], s[4], t6, s[5]);
+                } else
                 printf("  %d      %8.0f %8.0f %8.0f %8.0f %8.0f    | %6.0f\n", layer, s[0], s[1], s[2], s[3], s[4], s[5]);
             }
         }
