@@ -452,12 +452,13 @@ def selfcheck_multi(torch, dist, Q, dev, rank, world):
     for t in range(8):
         e_pk.step_tensor(acts[t][first:first + count].contiguous(), obs_out=g_pk.local_slot())
         full_pk = g_pk.gather()
-    rows = full_pk.view(-1, 4, 32, 8, 2).permute(0, 2, 1, 3, 4).reshape(-1, 32, 2)[:total].contiguous().view(torch.int16).reshape(total, 32)
+    ch = (e_pk.state_len + 7) // 8  # K chunks that travel: 3 for the 24-wide row = 48 B per env
+    rows = full_pk.view(-1, ch, 32, 8, 2).permute(0, 2, 1, 3, 4).reshape(-1, 8 * ch, 2)[:total].contiguous().view(torch.int16).reshape(total, 8 * ch)
     want = torch.zeros((total, 32), device=dev)
     want[:, :e_pk.state_len] = full_p2p
     want[:, e_pk.state_len] = 1.0
     pol = Q.MlpPolicy.from_npz(device=dev)
-    ok_packed = bool(torch.equal(rows, want.to(torch.bfloat16).view(torch.int16))) and \
+    ok_packed = bool(torch.equal(rows, want[:, :8 * ch].to(torch.bfloat16).view(torch.int16))) and \
         bool(torch.equal(pol.forward_packed(full_pk, total, deterministic=True), pol.forward(full_p2p, deterministic=True)))
     e_pk.close()
     ok_shard = True
@@ -517,13 +518,13 @@ def config4(torch, dist, Q, L, dev, rank, world, local, steps, barrier, peak, to
                "gather": {"none": "no collective (data-parallel policy)", "nccl": "step kernel writes the send slot; in-place "
                           "ncclAllGather", "p2p": "fused: step kernel bulk-stores its tiles into every peer (symmetric memory), "
                           "double-buffered, one barrier", "p2p_bf16": "fused, observations packed as BF16 in the on-device "
-                          "policy's operand layout (64 B per env instead of 96; qs_set_obs_format), consumed by "
+                          "policy's operand layout (48 B per env instead of 96; qs_set_obs_format), consumed by "
                           "qs_policy_forward_packed"}[mode],
                "value": total / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "envs_per_gpu": count,
                "launch": t.launch_mode, "replay_ms_per_step": rep,
                "per_gpu_roofline_frac": count * bpe / (ms * 1e-3) / 1e9 / peak,
                "nvlink_algorithmic_rx_bytes_per_gpu_per_step": 0 if gather is None else
-               (total - count) * (64 if mode == "p2p_bf16" else env.state_len * 4)}
+               (total - count) * (16 * ((env.state_len + 7) // 8) if mode == "p2p_bf16" else env.state_len * 4)}
         if nv0 and nv1:
             rec["nvlink_measured_bytes_per_step_rank0"] = {"tx": (nv1[0] - nv0[0]) * 1024 / steps, "rx": (nv1[1] - nv0[1]) * 1024 / steps}
             if gather is not None:

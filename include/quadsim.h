@@ -119,14 +119,15 @@ int qs_set_env_offset(qs_env *env, int64_t global_index_of_env0);   /* shard of 
 int qs_set_obs_peers(qs_env *env, int n_peers, void *const *peer_obs_bases, int64_t row_offset);
 /* Observation format of the DEVICE entry points (qs_step / qs_reset_all / qs_observe) for a consumer that is the
  * on-device policy and nothing else (config 4: the gathered observations only feed `model.predict`, `:803`):
- * QS_OBS_BF16_K32 makes obs_dev (and the peer buffers) a packed buffer of qs_obs_packed_bytes(n) bytes -- one 2 KB
- * block per 32 envs, [K chunk 0..3][row 0..31][8 x BF16], i.e. the first layer's A operand of qs_policy_forward_packed
- * (observation values, then the constant 1 of the folded bias, then zeros): 64 B per env over NVLink instead of
- * 96 (E2E) / 68 (INDI).  Needs obs_len <= 31; with peers, row_offset % 128 == 0.  The host-buffer entry points
- * (qs_step_host ...) and qs_rollout keep the reference's float32 rows and refuse a packed env. */
+ * QS_OBS_BF16_K32 makes obs_dev (and the peer buffers) a packed buffer of qs_obs_packed_bytes(obs_len, n) bytes: one
+ * block per 32 envs, [K chunk 0..chunks-1][row 0..31][8 x BF16] with chunks = ceil(obs_len / 8), i.e. the columns of the
+ * first layer's A operand of qs_policy_forward_packed that carry observation values (a trailing chunk that would hold
+ * only the constant 1 of the folded bias is synthesised by the policy kernel): 48 B per env over NVLink instead of
+ * 96 (E2E, gates_ahead = 1) / 68 (INDI).  Needs obs_len <= 31; with peers, row_offset % 128 == 0.  The host-buffer
+ * entry points (qs_step_host ...) and qs_rollout keep the reference's float32 rows and refuse a packed env. */
 typedef enum { QS_OBS_F32 = 0, QS_OBS_BF16_K32 = 1 } qs_obs_format;
 int qs_set_obs_format(qs_env *env, int format);
-int64_t qs_obs_packed_bytes(int64_t num_envs);
+int64_t qs_obs_packed_bytes(int obs_len, int64_t num_envs);
 int qs_enable_stats(qs_env *env, int on);
 int qs_get_stats(qs_env *env, qs_stats *out, int reset_after_read); /* synchronises                              */
 
@@ -223,7 +224,7 @@ int qs_policy_set_env_offset(qs_policy *policy, int64_t global_index_of_env0);
  * deterministic != 0 skips the noise (`nn_controller.c:5`).  Asynchronous on the policy's stream. */
 int qs_policy_forward(qs_policy *policy, const float *obs_dev, int64_t n, float *actions_dev, float *mean_dev,
                       float *raw_dev, int deterministic);
-/* the same forward over a QS_OBS_BF16_K32 buffer (n envs, qs_obs_packed_bytes(n) bytes, 16-byte aligned): the packed
+/* the same forward over a QS_OBS_BF16_K32 buffer (n envs, qs_obs_packed_bytes(in_dim, n) bytes, 16-byte aligned): the packed
  * blocks are TMA-loaded into the first MMA's operand buffer as they are.  Same actions as qs_policy_forward on the
  * float32 rows they were packed from, bit for bit.  Needs in_dim <= 31. */
 int qs_policy_forward_packed(qs_policy *policy, const void *packed_obs_dev, int64_t n, float *actions_dev, float *mean_dev,

@@ -59,7 +59,7 @@ SIGNATURES = {
     "qs_set_env_offset": (C.c_int, [_vp, C.c_int64]),
     "qs_set_obs_peers": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.c_int64]),
     "qs_set_obs_format": (C.c_int, [_vp, C.c_int]),
-    "qs_obs_packed_bytes": (C.c_int64, [C.c_int64]),
+    "qs_obs_packed_bytes": (C.c_int64, [C.c_int, C.c_int64]),
     "qs_enable_stats": (C.c_int, [_vp, C.c_int]),
     "qs_get_stats": (C.c_int, [_vp, C.POINTER(QsStats), C.c_int]),
     "qs_set_state": (C.c_int, [_vp, C.c_int64, C.c_int64, _fp, _fp, _i64p, _i64p]),

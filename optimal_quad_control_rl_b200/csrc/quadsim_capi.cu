@@ -363,7 +363,10 @@ int qs_set_obs_format(qs_env *e, int format) {
     e->P.obs_packed = format == QS_OBS_BF16_K32 ? 1 : 0;
     return QS_OK;
 }
-int64_t qs_obs_packed_bytes(int64_t n) { return n <= 0 ? 0 : (n + qs::kPolRows - 1) / qs::kPolRows * (4 * (int64_t)qs::kPackBlock); }
+int64_t qs_obs_packed_bytes(int obs_len, int64_t n) {
+    if (n <= 0 || obs_len < 1 || obs_len > qs::kPackK - 1) return 0;
+    return (n + qs::kPolRows - 1) / qs::kPolRows * (4 * (int64_t)qs::pack_block_bytes(obs_len));
+}
 
 int qs_enable_stats(qs_env *e, int on) { QS_CHECK_ENV(e); e->stats_on = on != 0; return QS_OK; }
 

@@ -85,7 +85,7 @@ struct StepParams {
     unsigned long long *epoch;
     int n_gates, gates_ahead, obs_len;
     // 0: observations leave as float32 rows (N, obs_len), the reference's layout.  1: as BF16 in the on-device policy's
-    // A-operand layout (pack_obs_row / kPackBlock below) -- `obs` and `peer_obs` then point to packed buffers
+    // A-operand layout (pack_obs_row / pack_block_bytes below) -- `obs` and `peer_obs` then point to packed buffers
     int obs_packed;
     int mode, reset_source;
     int l2_hints;  // 1: state evict_last, streams evict_first (see l2_policy_*); 0: no cache hints
@@ -369,13 +369,17 @@ __device__ __forceinline__ void store_obs_tile(float *dst, const float *s_obs, i
 }
 
 // ---- packed observations: what the step hands to the on-device policy when nobody needs float32 rows (a sharded job
-// whose policy reads the all-gathered observations, BASELINE.json config 4).  One 2 KB block per 32 envs:
-//   [K chunk c = 0..3][row r = 0..31][8 x BF16]      = the policy kernel's K-major A-operand slabs for its first layer
-// (K = 32 columns: obs_len <= 31 values, the constant 1 that multiplies the folded bias at column obs_len, zeros
-// after it), 64 B per env instead of 96 / 68 B of float32 -- a third less to move through NVLink, and the policy loads
-// it with TMA straight into the MMA's operand buffer (no load / convert / store instructions at all).
+// whose policy reads the all-gathered observations, BASELINE.json config 4).  One block per 32 envs:
+//   [K chunk c = 0 .. chunks-1][row r = 0..31][8 x BF16]     = the policy kernel's K-major A-operand slabs, first layer
+// The operand has kPackK = 32 columns: obs_len <= 31 values, the constant 1 that multiplies the folded bias at column
+// obs_len, zeros after it.  Only the chunks that carry an observation value travel: chunks = ceil(obs_len / 8) -- the
+// E2E row of 24 values is 3 chunks = 48 B per env instead of 96 B of float32, half the bytes through NVLink; a chunk that
+// would hold nothing but the constant (obs_len % 8 == 0) is written by the policy kernel itself.  The policy loads
+// the blocks with TMA straight into the MMA's operand buffer (no load / convert / store instructions at all).
 constexpr int kPackK = 32;
-constexpr int kPackBlock = (kPackK / 8) * 32 * 16;  // 2048 B per 32 envs
+constexpr int kPackChunkBytes = 32 * 16;  // one K chunk of a block: 32 rows x 8 BF16
+__host__ __device__ constexpr int pack_chunks(int obs_len) { return (obs_len + 7) / 8; }
+__host__ __device__ constexpr int pack_block_bytes(int obs_len) { return pack_chunks(obs_len) * kPackChunkBytes; }
 __device__ __forceinline__ uint32_t pack_bf16_rn(float lo, float hi) {  // round-to-nearest-even, lo in the low half
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -731,7 +735,7 @@ template <int V> struct Stage : Blk<V> {
 constexpr int kBarBytes = 128;  // mbarriers live in the first 128 bytes of dynamic shared memory
 constexpr int kWarps = kBlock / 32;
 
-// a warp's observation staging slice: its 32 float32 rows, and never less than one packed BF16 block (kPackBlock)
+// a warp's observation staging slice: its 32 float32 rows, and never less than the largest packed BF16 block (2 KB)
 __host__ __device__ constexpr int step_slice_floats(int obs_len) { return 32 * obs_len > 512 ? 32 * obs_len : 512; }
 __host__ __device__ constexpr size_t step_smem_bytes(int variant, int stages, int obs_len, int n_gates) {
     return kBarBytes + (size_t)stages * kWarps * (variant == kE2E ? (int)Stage<kE2E>::BYTES : (int)Stage<kINDI>::BYTES) +
@@ -939,18 +943,19 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
                 __syncwarp();  // every lane has read its float32 row: the block is built over them
                 uint4 *blk = reinterpret_cast<uint4 *>(warp_obs);
 #pragma unroll
-                for (int c = 0; c < kPackK / 8; ++c) blk[c * 32 + lane] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+                for (int c = 0; c < kPackK / 8; ++c)
+                    if (c < pack_chunks(P.obs_len)) blk[c * 32 + lane] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
                     const long long b32 = tile * kWarps + warp;  // 32-env block index within this launch's env range
-                    unsigned char *pk = reinterpret_cast<unsigned char *>(P.obs) + b32 * (long long)kPackBlock;
-                    if (kHints) bulk_store_hint(pk, warp_obs, kPackBlock, pol_stream);
-                    else bulk_store(pk, warp_obs, kPackBlock);
+                    const uint32_t pkb = (uint32_t)pack_block_bytes(P.obs_len);
+                    unsigned char *pk = reinterpret_cast<unsigned char *>(P.obs) + b32 * (long long)pkb;
+                    if (kHints) bulk_store_hint(pk, warp_obs, pkb, pol_stream);
+                    else bulk_store(pk, warp_obs, pkb);
 #pragma unroll 1
                     for (int p = 0; p < P.n_peers; ++p)
-                        bulk_store(reinterpret_cast<unsigned char *>(P.peer_obs[p]) + ((P.peer_row_offset >> 5) + b32) * (long long)kPackBlock,
-                                   warp_obs, kPackBlock);
+                        bulk_store(reinterpret_cast<unsigned char *>(P.peer_obs[p]) + ((P.peer_row_offset >> 5) + b32) * (long long)pkb, warp_obs, pkb);
                 }
                 obs_in_flight = true;
                 if (P.stats && active) {
@@ -1066,9 +1071,10 @@ __global__ void __launch_bounds__(kBlock) observe_kernel(const __grid_constant__
     if (P.obs_packed) {  // packed blocks: four coalesced 512-byte stores per warp, straight from registers
         uint32_t w[16];
         pack_obs_row(s_obs + threadIdx.x * P.obs_len, P.obs_len, env < P.n, w);
-        uint4 *blk = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(P.obs) + (env >> 5) * (long long)kPackBlock);
+        uint4 *blk = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(P.obs) + (env >> 5) * (long long)pack_block_bytes(P.obs_len));
 #pragma unroll
-        for (int c = 0; c < kPackK / 8; ++c) blk[c * 32 + (threadIdx.x & 31)] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+        for (int c = 0; c < kPackK / 8; ++c)
+            if (c < pack_chunks(P.obs_len)) blk[c * 32 + (threadIdx.x & 31)] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
         if (reset_all && threadIdx.x == 0) epoch_arrive(P);
         return;
     }

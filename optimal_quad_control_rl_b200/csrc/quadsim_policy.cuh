@@ -34,7 +34,7 @@ constexpr int kPolOnes = kPolHidden - 1;  // hidden unit that carries the consta
 constexpr int kSlab = kPolRows * 16;      // one K-chunk of 8 BF16 for 128 rows: 2 KB
 
 struct PolicyParams {
-    const float *obs;         // (n, in_dim) f32 row-major; with obs_packed: the step kernel's packed BF16 blocks (kPackBlock)
+    const float *obs;         // (n, in_dim) f32 row-major; with obs_packed: the step kernel's packed BF16 blocks (pack_block_bytes)
     int obs_packed;           // 1: `obs` already holds the first layer's A operand (k1 <= kPackK): TMA-loaded, nothing converted
     float *actions;           // (n, 4) f32: clip(mean + std * N(0,1), -1, 1)
     float *mean;              // (n, 4) f32 network output before noise, or NULL
@@ -279,14 +279,18 @@ __global__ void __launch_bounds__(4 * kPolRows, 1) policy_kernel(const __grid_co
         // ---- A operand of layer 1.  Packed observations (the step kernel's BF16 blocks, one per 32 rows) ARE the operand:
         // sixteen 512-byte TMA copies put the tile's four K-chunk slabs in place; nobody loads, converts or stores a value.
         if (P.obs_packed) {
+            const int chunks = pack_chunks(P.in_dim);  // the chunks that travel; a pure-constant chunk behind them is made here
             if (tid == 0) {
-                mbar_expect_tx(bar_obs, (uint32_t)(P.k1 / 8) * kSlab);  // k1 <= kPackK: a narrow first layer reads the first chunks only
-                const unsigned char *src = reinterpret_cast<const unsigned char *>(P.obs) + tile * (long long)(4 * kPackBlock);
+                mbar_expect_tx(bar_obs, (uint32_t)chunks * kSlab);
+                const uint32_t pkb = (uint32_t)pack_block_bytes(P.in_dim);
+                const unsigned char *src = reinterpret_cast<const unsigned char *>(P.obs) + tile * (long long)(4 * pkb);
 #pragma unroll
                 for (int b = 0; b < 4; ++b)
-                    for (int c = 0; c < P.k1 / 8; ++c)
-                        bulk_load(s_a + c * kSlab + b * 512, src + b * kPackBlock + c * 512, 512u, bar_obs);
+                    for (int c = 0; c < chunks; ++c)
+                        bulk_load(s_a + c * kSlab + b * 512, src + b * pkb + c * 512, 512u, bar_obs);
             }
+            for (int c = chunks; c < P.k1 / 8; ++c)  // chunks without an observation value: zeros, or (in_dim % 8 == 0) the
+                *reinterpret_cast<uint4 *>(s_a + c * kSlab + tid * 16) = make_uint4(c * 8 == P.in_dim ? 0x3F80u : 0u, 0u, 0u, 0u);  // bias' constant 1
             mbar_wait(bar_obs, obs_phase);
             obs_phase ^= 1u;
         } else {

@@ -519,7 +519,7 @@ class _QuadGatesBase(_VecEnvBase):
     @obs_format.setter
     def obs_format(self, fmt):
         """``"f32"``: float32 rows (N, D), the reference's layout.  ``"bf16_k32"``: packed BF16 blocks in the on-device policy's
-        operand layout (`qs_set_obs_format`; 64 B per env) for a sharded job whose gathered observations only feed
+        operand layout (`qs_set_obs_format`; 48 B per env for the 24-wide E2E row) for a sharded job whose gathered observations only feed
         ``MlpPolicy.forward_packed``.  In that format ``step_tensor`` / ``reset_tensor`` need ``obs_out=`` (a uint8 CUDA
         tensor of ``packed_obs_bytes()`` bytes) and the NumPy-facing ``step`` / ``reset`` / ``rollout`` are unavailable."""
         if fmt not in ("f32", "bf16_k32"):
@@ -528,7 +528,7 @@ class _QuadGatesBase(_VecEnvBase):
         self._obs_format = fmt
 
     def packed_obs_bytes(self, n=None):
-        return int(self._lib.qs_obs_packed_bytes(int(self.num_envs if n is None else n)))
+        return int(self._lib.qs_obs_packed_bytes(int(self.state_len), int(self.num_envs if n is None else n)))
 
     def enable_stats(self, on=True):
         self._call("qs_enable_stats", int(on))

@@ -123,7 +123,7 @@ class MlpPolicy:
         on the float32 rows."""
         if packed_obs.dtype != torch.uint8 or not packed_obs.is_cuda or not packed_obs.is_contiguous():
             raise ValueError("forward_packed needs a contiguous uint8 CUDA tensor (packed BF16 observation blocks)")
-        need = self._lib.qs_obs_packed_bytes(int(n))
+        need = self._lib.qs_obs_packed_bytes(int(self.in_dim), int(n))
         if packed_obs.numel() < need:
             raise ValueError(f"packed observations of {n} envs take {need} bytes, got {packed_obs.numel()}")
         if out is None:

@@ -60,11 +60,11 @@ class ObsPeerGather:
     barrier t, consumers of t, step t+1, barrier t+1, ...).  So nobody overwrites a buffer a peer still reads, as long
     as the consumers run on the stream ``gather()`` was called on."""
 
-    PACK_TILE, PACK_TILE_BYTES = 128, 8192  # packed format: 4 blocks of 32 envs x 2 KB per 128-env policy tile
+    PACK_TILE = 128  # packed format: 4 blocks of 32 envs per 128-env policy tile, ceil(obs_len / 8) x 512 B each
 
     def __init__(self, total_envs, obs_len, device, group=None, packed=False):
         """``packed=True``: the buffers hold the step kernel's packed BF16 blocks (``env.obs_format = "bf16_k32"``,
-        64 B per env over NVLink instead of ``4 * obs_len``) for ``MlpPolicy.forward_packed``; every rank's slice must
+        ``16 * ceil(obs_len / 8)`` B per env over NVLink instead of ``4 * obs_len``) for ``MlpPolicy.forward_packed``; every rank's slice must
         then start on a multiple of 128 envs."""
         import torch.distributed._symmetric_memory as symm_mem
         self.group = group if group is not None else dist.group.WORLD
@@ -73,6 +73,7 @@ class ObsPeerGather:
         self.first, self.count = shard_range(total_envs, self.rank, self.world)
         self.packed = bool(packed)
         self.total_envs = int(total_envs)
+        self.PACK_TILE_BYTES = 4 * ((int(obs_len) + 7) // 8) * 512
         if self.packed:
             if any(shard_range(total_envs, r, self.world)[0] % self.PACK_TILE for r in range(self.world)):
                 raise ValueError("ObsPeerGather(packed=True): every rank's slice must start on a multiple of 128 envs")

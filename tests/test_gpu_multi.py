@@ -42,7 +42,7 @@ for t in range(8):
     full_p2p = g_p2p.gather().clone()
     assert torch.equal(full_nccl, full_p2p), (rank, t)
     assert full_p2p.abs().sum().item() > 0                 # no extra barrier: ObsPeerGather double-buffers
-# the packed BF16 gather (64 B per env over NVLink): same envs, the gathered buffer is the policy's operand as it is
+# the packed BF16 gather (48 B per env over NVLink): same envs, the gathered buffer is the policy's operand as it is
 e_pk = make()
 g_pk = Q.ObsPeerGather(total, e_pk.state_len, dev, packed=True)
 g_pk.attach(e_pk)
@@ -52,14 +52,15 @@ for t in range(8):
     a = acts[t][first:first + count].contiguous()
     e_pk.step_tensor(a, obs_out=g_pk.local_slot())
     full_pk = g_pk.gather()
-    blocks = full_pk.view(-1, 4, 32, 8, 2)                                         # [32-env block][chunk][row][8 x bf16 as 2 bytes]
-    rows = blocks.permute(0, 2, 1, 3, 4).reshape(-1, 32, 2)[:total].contiguous().view(torch.int16).reshape(total, 32)
+    ch = (e_pk.state_len + 7) // 8                                                 # chunks that travel (24 values: 3, 48 B per env)
+    blocks = full_pk.view(-1, ch, 32, 8, 2)                                        # [32-env block][chunk][row][8 x bf16 as 2 bytes]
+    rows = blocks.permute(0, 2, 1, 3, 4).reshape(-1, 8 * ch, 2)[:total].contiguous().view(torch.int16).reshape(total, 8 * ch)
 torch.cuda.synchronize()
 # (the float32 reference of the LAST step: full_p2p, gathered above from identically seeded envs)
 want = torch.zeros((total, 32), device=dev)
 want[:, :e_pk.state_len] = full_p2p
 want[:, e_pk.state_len] = 1.0
-assert torch.equal(rows, want.to(torch.bfloat16).view(torch.int16)), "packed gather != pack(float32 gather)"
+assert torch.equal(rows, want[:, :8 * ch].to(torch.bfloat16).view(torch.int16)), "packed gather != pack(float32 gather)"
 a_pk = pol.forward_packed(full_pk, total, deterministic=True)
 a_f32 = pol.forward(full_p2p, deterministic=True)
 assert torch.equal(a_pk, a_f32), "policy on the packed gather != policy on the float32 gather"

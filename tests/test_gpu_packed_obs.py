@@ -8,15 +8,17 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def unpack(buf, n):
-    """(n, 32) int16 view of the BF16 rows of a packed buffer: [32-env block][chunk 0..3][row 0..31][8 x bf16]."""
+def unpack(buf, n, obs_len):
+    """(n, 8 * chunks) int16 view of the BF16 rows of a packed buffer: [32-env block][chunk 0..chunks-1][row 0..31][8 x bf16],
+    chunks = ceil(obs_len / 8) (the chunks that carry an observation value)."""
     import torch
-    blocks = buf.view(-1, 4, 32, 8, 2)
-    return blocks.permute(0, 2, 1, 3, 4).reshape(-1, 32, 2)[:n].contiguous().view(torch.int16).reshape(n, 32)
+    ch = (obs_len + 7) // 8
+    blocks = buf.view(-1, ch, 32, 8, 2)
+    return blocks.permute(0, 2, 1, 3, 4).reshape(-1, 8 * ch, 2)[:n].contiguous().view(torch.int16).reshape(n, 8 * ch)
 
 
 @pytest.mark.parametrize("variant,ga,n", [("e2e", 1, 4096), ("e2e", 1, 1000), ("e2e", 0, 130), ("e2e", 2, 5000),
-                                          ("indi", 1, 4096), ("indi", 0, 777), ("indi", 4, 2049)])
+                                          ("indi", 1, 4096), ("indi", 0, 777), ("indi", 4, 2049), ("indi", 3, 640)])
 def test_packed_observations_equal_packed_float32_rows(variant, ga, n, tracks):
     import torch
     import optimal_quad_control_rl_b200 as Q
@@ -41,14 +43,16 @@ def test_packed_observations_equal_packed_float32_rows(variant, ga, n, tracks):
     pol2 = Q.MlpPolicy(w, b, std=np.full(4, 0.3, np.float32), seed=3)
 
     def check(of, what):
+        ch = (D + 7) // 8
         want = torch.zeros((n, 32), device="cuda")
         want[:, :D] = of
-        want[:, D] = 1.0
-        assert torch.equal(unpack(pk, n), want.to(torch.bfloat16).view(torch.int16)), what
-        tail = pk[(n + 31) // 32 * 2048:]
+        want[:, D] = 1.0  # (lands in a travelling chunk unless D % 8 == 0: then the policy kernel writes it itself)
+        assert torch.equal(unpack(pk, n, D), want[:, :8 * ch].to(torch.bfloat16).view(torch.int16)), what
+        blk = ch * 512
+        tail = pk[(n + 31) // 32 * blk:]
         assert int(tail.abs().sum()) == 0, "blocks beyond the last env must stay zero"
         if n % 32:  # rows of the last block beyond n are zero
-            last = pk[(n // 32) * 2048:(n // 32 + 1) * 2048].view(4, 32, 16)
+            last = pk[(n // 32) * blk:(n // 32 + 1) * blk].view(ch, 32, 16)
             assert int(last[:, n % 32:].abs().sum()) == 0
         a0 = pol.forward(of, deterministic=True).clone()
         a1 = pol.forward_packed(pk, n, deterministic=True).clone()

@@ -1,5 +1,2 @@
-bash tools/gpu.sh check e1
-bash tools/gpu.sh numpy e1
-bash tools/gpu.sh ncu e1
-bash tools/gpu.sh ncu-tc e1
-bash tools/gpu.sh bench e1
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 | tee gpurun_out/e3_pytest.log
+bash tools/gpu.sh multi e3 2
