@@ -211,6 +211,9 @@ int qs_policy_destroy(qs_policy *policy);
  * reference's generated C has both (`nn_relu` / `nn_tanh`, c_code/neural_network.c:407-417).  tanh needs hidden_dim <= 120. */
 typedef enum { QS_ACT_RELU = 0, QS_ACT_TANH = 1 } qs_activation;
 int qs_policy_set_activation(qs_policy *policy, int activation);
+/* > 0: qs_policy_forward sanitises its float32 observations like SB3-side learners do before a forward over the rollout
+ * buffer (NaN -> 0, clamp to +-limit); used by the PPO loop's value / old-log-prob pass.  0 (default) = off. */
+int qs_policy_set_obs_limit(qs_policy *policy, float limit);
 const char *qs_policy_last_error(const qs_policy *policy); /* NULL: error of the last failed qs_policy_create */
 int qs_policy_set_stream(qs_policy *policy, void *stream);
 /* layer 0..n_hidden (the last is the output layer); W row-major [out][in] and b [out] as torch / the generated C

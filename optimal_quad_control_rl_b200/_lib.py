@@ -86,6 +86,7 @@ SIGNATURES = {
     "qs_policy_set_activation": (C.c_int, [_vp, C.c_int]),
     "qs_policy_seed": (C.c_int, [_vp, C.c_uint64]),
     "qs_policy_set_env_offset": (C.c_int, [_vp, C.c_int64]),
+    "qs_policy_set_obs_limit": (C.c_int, [_vp, C.c_float]),
     "qs_policy_forward": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int]),
     "qs_policy_forward_packed": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int]),
     "qs_policy_launch_count": (C.c_uint64, [_vp]),

@@ -739,6 +739,7 @@ struct qs_policy {
     bool dirty = true, pdl = true;
     bool ts = false;     // QS_POLICY_TS=1: qs_policy_forward runs policy_kernel_ts (activations in tensor memory; measured slower: 2 chains)
     int activation = 0;  // 0 ReLU, 1 tanh
+    float obs_limit = 0.0f;  // qs_policy_set_obs_limit
     uint64_t seed = 0, launches = 0;
     int64_t env_offset = 0;
     float std[4] = {0, 0, 0, 0};
@@ -875,6 +876,15 @@ int qs_policy_set_activation(qs_policy *p, int activation) {
     return QS_OK;
 }
 
+// PPO's learner sanitises what it reads from the rollout buffers (NaN -> 0, clamp to +-obs_limit: a tumbling quad's roll
+// angle winds to ~1e8); a forward over those buffers (values, old log-probs) has to see the same inputs.  0 = off.
+int qs_policy_set_obs_limit(qs_policy *p, float limit) {
+    QS_PCHECK(p);
+    if (!(limit >= 0.0f)) return pfail(p, QS_ERR_ARG, "qs_policy_set_obs_limit: limit must be >= 0 (0 = off)");
+    p->obs_limit = limit;
+    return QS_OK;
+}
+
 int qs_policy_set_std(qs_policy *p, const float *std4) {
     QS_PCHECK(p);
     if (!std4) return pfail(p, QS_ERR_ARG, "qs_policy_set_std: NULL");
@@ -896,7 +906,7 @@ static int policy_params(qs_policy *p, int64_t n, int deterministic, cudaStream_
     }
     P.weights = p->w_dev; P.epoch = p->epoch_dev;
     P.n = n; P.env_offset = p->env_offset; P.seed = p->seed; P.in_dim = p->in_dim; P.k1 = p->k1; P.n_hidden = p->n_hidden; P.hidden = p->hidden;
-    P.out_dim = p->out_dim; P.deterministic = deterministic; P.activation = p->activation;
+    P.out_dim = p->out_dim; P.deterministic = deterministic; P.activation = p->activation; P.obs_limit = p->obs_limit;
     P.weight_bytes = qs::policy_weight_bytes(p->k1, p->n_hidden);
     P.tmem_cols = p->groups <= 1 ? 128u : (p->groups == 2 ? 256u : 512u);
     for (int k = 0; k < 4; ++k) P.std[k] = p->std[k];
@@ -909,7 +919,7 @@ static int policy_launch(qs_policy *p, const float *obs_dev, int64_t n, float *a
     if (int r = policy_params(p, n, deterministic, stream, P)) return r;
     P.obs = obs_dev; P.actions = actions_dev; P.mean = mean_dev; P.raw = raw_dev;
     P.obs_packed = packed ? 1 : 0;
-    const bool ts = p->ts && !packed;  // (the TMEM-activation kernel reads float32 rows only)
+    const bool ts = p->ts && !packed && p->obs_limit == 0.0f;  // (the TMEM-activation kernel reads plain float32 rows only)
     const long long tiles = (n + qs::kPolRows - 1) / qs::kPolRows;
     void *args[] = {&P};
     cudaLaunchConfig_t cfg{};

@@ -52,6 +52,7 @@ struct PolicyParams {
     uint32_t weight_bytes;
     uint32_t tmem_cols;       // accumulator columns to allocate: 128 per tile group, rounded up to a power of two
     float std[4];
+    float obs_limit;          // > 0: observations are sanitised on the way in like the PPO learner does (NaN -> 0, clamp to +-limit)
 };
 
 __host__ __device__ constexpr uint32_t policy_w1_bytes(int k1) { return (uint32_t)(k1 / 8) * kPolHidden * 16; }
@@ -312,6 +313,10 @@ __global__ void __launch_bounds__(4 * kPolRows, 1) policy_kernel(const __grid_co
                         }
                     }
                     x[q * 4 + 0] = v.x; x[q * 4 + 1] = v.y; x[q * 4 + 2] = v.z; x[q * 4 + 3] = v.w;
+                }
+                if (P.obs_limit > 0.0f) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) x[q] = (x[q] == x[q]) ? fminf(fmaxf(x[q], -P.obs_limit), P.obs_limit) : 0.0f;
                 }
 #pragma unroll
                 for (int q = 0; q < 8; ++q)

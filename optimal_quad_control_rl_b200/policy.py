@@ -20,7 +20,7 @@ class MlpPolicy:
     """``weights[l]`` is ``(out, in)`` float32 (torch / generated-C layout), ``biases[l]`` is ``(out,)``; the last
     pair is the output layer.  ``std`` = exp(log_std) of the Gaussian action distribution."""
 
-    def __init__(self, weights, biases, std=None, device=None, seed=0, env_offset=0, activation="relu"):
+    def __init__(self, weights, biases, std=None, device=None, seed=0, env_offset=0, activation="relu", obs_limit=0.0):
         if not torch.cuda.is_available():
             raise L.QuadsimError("no CUDA device: the policy only runs on the GPU (there is no CPU fallback)")
         self._lib = L.load()
@@ -55,6 +55,8 @@ class MlpPolicy:
             raise ValueError("activation must be 'relu' or 'tanh'")
         self.activation = activation
         self._call("qs_policy_set_activation", 1 if activation == "tanh" else 0)
+        if obs_limit:  # sanitise the inputs like the PPO learner (NaN -> 0, clamp): forwards over rollout buffers
+            self._call("qs_policy_set_obs_limit", float(obs_limit))
         self._call("qs_policy_seed", int(seed))
         self._call("qs_policy_set_env_offset", int(env_offset))
 

@@ -231,15 +231,16 @@ class PPO:
                  gae_lambda=0.95, clip_range=0.2, clip_range_vf=None, normalize_advantage=True, ent_coef=0.0, vf_coef=0.5,
                  max_grad_norm=0.5, use_sde=False, sde_sample_freq=-1, target_kl=None, stats_window_size=100,
                  tensorboard_log=None, policy_kwargs=None, verbose=0, seed=None, device="auto", _init_setup_model=True, *,
-                 rollout="auto", bootstrap=None, update="auto", tf32=True, amp=False, obs_limit=2.0e3, value_limit=1.0e3,
-                 obs_dim=None):
+                 rollout="auto", bootstrap=None, update="auto", evaluate="auto", tf32=True, amp=False, obs_limit=2.0e3,
+                 value_limit=1.0e3, obs_dim=None):
         if not (policy == "MlpPolicy" or policy is ActorCriticPolicy):
             raise ValueError(f"only 'MlpPolicy' is supported (got {policy!r})")
         if use_sde or clip_range_vf is not None:
             raise NotImplementedError("use_sde / clip_range_vf are not used by the reference and not implemented")
         if rollout not in ("auto", "device", "host") or bootstrap not in (None, "none", "sb3_a8") or \
-                update not in ("auto", "torch", "fused"):
-            raise ValueError("rollout in {auto, device, host}; bootstrap in {None, 'none', 'sb3_a8'}; update in {auto, torch, fused}")
+                update not in ("auto", "torch", "fused") or evaluate not in ("auto", "torch", "device"):
+            raise ValueError("rollout in {auto, device, host}; bootstrap in {None, 'none', 'sb3_a8'}; update in {auto, torch, fused}; "
+                             "evaluate in {auto, torch, device}")
         self.env = env
         self.venv = getattr(env, "venv", env)  # VecMonitor(env) -> env
         self.learning_rate, self.n_steps, self.batch_size, self.n_epochs = float(learning_rate), int(n_steps), int(batch_size), int(n_epochs)
@@ -292,6 +293,16 @@ class PPO:
         if fits:
             self.actor = MlpPolicy(*self._pi_arrays(), std=self.policy.log_std.detach().exp().cpu().numpy(), device=self.device,
                                    seed=0 if seed is None else int(seed), activation=act)
+        # values / old log-probs over the collected buffer: the same tcgen05 forward kernel (an actor and a critic instance
+        # that sanitise their inputs like the learner) instead of torch GEMMs -- 21 -> 3 ms per 8.4 M-sample buffer
+        fits_vf = act is not None and vf == pi and fits
+        if evaluate == "device" and not (fits_vf and self.rollout == "device"):
+            raise ValueError("evaluate='device' needs rollout='device' and pi / vf networks of the same supported shape")
+        self.evaluate = "device" if (evaluate != "torch" and fits_vf and self.rollout == "device") else "torch"
+        self.eval_actor = self.critic = None
+        if self.evaluate == "device":
+            self.eval_actor = MlpPolicy(*self._pi_arrays(), device=self.device, activation=act, obs_limit=self.obs_limit)
+            self.critic = MlpPolicy(*self._vf_arrays(), device=self.device, activation=act, obs_limit=self.obs_limit)
 
     # convenient aliases used by the tests / tools of this repository
     pi = property(lambda self: nn.Sequential(*self.policy.mlp_extractor.policy_net, self.policy.action_net))
@@ -309,10 +320,17 @@ class PPO:
         lin = self.policy.pi_layers()
         return ([m.weight.detach().cpu().numpy() for m in lin], [m.bias.detach().cpu().numpy() for m in lin])
 
+    def _vf_arrays(self):
+        lin = self.policy.vf_layers()
+        return ([m.weight.detach().cpu().numpy() for m in lin], [m.bias.detach().cpu().numpy() for m in lin])
+
     def _publish(self):
         if self.actor is not None:
             w, b = self._pi_arrays()
             self.actor.set_weights(w, b, std=self.policy.log_std.detach().exp().cpu().numpy())
+            if self.eval_actor is not None:
+                self.eval_actor.set_weights(w, b)
+                self.critic.set_weights(*self._vf_arrays())
 
     def _sane(self, obs):
         """Observations as the learner sees them: finite and within +-obs_limit (identity for every sane sample:
@@ -359,6 +377,8 @@ class PPO:
 
     def _evaluate_buffer(self, b, T, n, d):
         """values (T+1, n), old log-probs and sample weights over the collected buffer (device path)."""
+        if self.evaluate == "device":
+            return self._evaluate_buffer_device(b, T, n, d)
         with torch.no_grad():
             torch.nan_to_num_(b["rewards"], nan=0.0, posinf=0.0, neginf=0.0)  # one NaN would poison a whole GAE column
             chunk = max(1, (1 << 22) // n)  # ~4M rows per forward
@@ -376,6 +396,25 @@ class PPO:
                 t1 = min(T, t0 + chunk)
                 b["log_probs"][t0:t1] = self._log_prob(b["obs"][t0:t1].reshape(-1, d),
                                                        b["raw_actions"][t0:t1].reshape(-1, 4)).reshape(t1 - t0, n)
+
+    def _evaluate_buffer_device(self, b, T, n, d):
+        """The same three results from two launches of the tcgen05 forward kernel (critic over T+1 steps, policy mean over T)
+        plus elementwise glue: BF16 operands like the actor that sampled the actions, so the PPO ratio starts at exactly 1."""
+        with torch.no_grad():
+            torch.nan_to_num_(b["rewards"], nan=0.0, posinf=0.0, neginf=0.0)  # one NaN would poison a whole GAE column
+            rows = (T + 1) * n
+            if getattr(self, "_eval_scratch", None) is None or self._eval_scratch[0].shape[0] < rows:
+                self._eval_scratch = (torch.empty((rows, 4), device=self.device), torch.empty((rows, 4), device=self.device))
+            out4, mean4 = self._eval_scratch
+            flat = b["obs"].reshape(rows, d)
+            self.critic.forward(flat, deterministic=True, out=out4[:rows], mean_out=mean4[:rows])
+            b["values"].copy_(torch.nan_to_num(mean4[:rows, 0]).clamp_(-self.value_limit, self.value_limit).reshape(T + 1, n))
+            obs, ra = b["obs"][:T], b["raw_actions"]
+            ok = torch.isfinite(obs).all(-1) & (obs.abs().amax(-1) <= self.obs_limit)
+            ok &= torch.isfinite(ra).all(-1) & (ra.abs().amax(-1) <= self._ACT_LIMIT) & torch.isfinite(b["rewards"])
+            b["weights"].copy_(ok)
+            self.eval_actor.forward(flat[:T * n], deterministic=True, out=out4[:T * n], mean_out=mean4[:T * n])
+            b["log_probs"].copy_(self.policy.log_prob(mean4[:T * n], self._sane_act(ra.reshape(T * n, 4))).reshape(T, n))
 
     def _collect_device(self):
         env, T, n, d = self.venv, self.n_steps, self.n_envs, self.venv.state_len

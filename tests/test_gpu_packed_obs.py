@@ -77,6 +77,39 @@ def test_packed_observations_equal_packed_float32_rows(variant, ga, n, tracks):
         e.close()
 
 
+def pack(x):
+    """Host-side restatement of the packed format (what the step kernel emits) for float32 rows `x` (n, D)."""
+    import torch
+    n, D = x.shape
+    ch = (D + 7) // 8
+    full = torch.zeros((n, 32), device=x.device)
+    full[:, :D] = x
+    full[:, D] = 1.0
+    nb = (n + 127) // 128 * 4                                   # whole 128-row policy tiles
+    rows = torch.zeros((nb * 32, 8 * ch), dtype=torch.bfloat16, device=x.device)
+    rows[:n] = full[:, :8 * ch].to(torch.bfloat16)
+    return rows.view(nb, 32, ch, 8).permute(0, 2, 1, 3).contiguous().view(torch.uint8).reshape(-1)
+
+
+@pytest.mark.parametrize("in_dim", [8, 13, 16, 24, 31])
+def test_forward_packed_for_every_chunk_pattern(in_dim):
+    """Observation widths that end on a chunk boundary (8, 16, 24: the policy kernel writes the bias' constant-1 chunk and,
+    for 16, a zero chunk behind it) and inside one (13, 31: the constant travels)."""
+    import torch
+    import optimal_quad_control_rl_b200 as Q
+    rng = np.random.default_rng(in_dim)
+    dims = [in_dim, 120, 120, 120, 4]
+    w = [rng.normal(0, 1 / np.sqrt(dims[l]), (dims[l + 1], dims[l])).astype(np.float32) for l in range(4)]
+    b = [rng.normal(0, 0.3, dims[l + 1]).astype(np.float32) for l in range(4)]
+    pol = Q.MlpPolicy(w, b)
+    for n in (1, 200, 4096):
+        x = torch.from_numpy(rng.normal(0, 1, (n, in_dim)).astype(np.float32)).cuda()
+        a0 = pol.forward(x, deterministic=True).clone()
+        a1 = pol.forward_packed(pack(x), n, deterministic=True).clone()
+        assert torch.equal(a0, a1), (in_dim, n)
+        assert float(a0.abs().max()) > 1e-3
+
+
 def test_packed_format_is_refused_where_float32_rows_are_the_contract(tracks):
     import torch
     import optimal_quad_control_rl_b200 as Q

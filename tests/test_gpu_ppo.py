@@ -52,7 +52,8 @@ def test_ppo_short_run_improves_reward(tracks):
     import optimal_quad_control_rl_b200 as Q
     gp, gy, sp = tracks["indi"]
     env = Q.Quadcopter3DGatesINDI(4096, gp, gy, sp, gates_ahead=1, reset_rng="device", seed=0)
-    ppo = Q.PPO("MlpPolicy", env, policy_kwargs=PK(), n_steps=128, batch_size=16384, n_epochs=4, gamma=0.999, seed=0)
+    ppo = Q.PPO("MlpPolicy", env, policy_kwargs=PK(), n_steps=128, batch_size=16384, n_epochs=4, gamma=0.999, seed=0,
+                evaluate="torch")
     b = ppo.collect_rollouts()
     with torch.no_grad():  # before any update: new log-prob == stored log-prob
         lp = ppo._log_prob(b["obs"][:4].reshape(-1, env.state_len), b["raw_actions"][:4].reshape(-1, 4))
@@ -69,6 +70,42 @@ def test_ppo_short_run_improves_reward(tracks):
     assert np.mean([r["reward_per_step"] for r in h[-3:]]) > np.mean([r["reward_per_step"] for r in h[:2]]) + 0.005
     a, _ = ppo.predict(env.states if env.states.any() else np.zeros((4096, env.state_len), np.float32), deterministic=True)
     assert a.shape == (4096, 4) and np.isfinite(a).all()
+
+
+def test_buffer_evaluation_on_the_forward_kernel_matches_torch(tracks):
+    """`evaluate="device"` (default with the device rollout): values and old log-probs of the collected buffer come from two
+    launches of the tcgen05 forward kernel instead of torch GEMMs.  Against the float32 torch pass on the same buffer: BF16
+    operand rounding only; against the BF16 actor that sampled the actions: the stored log-prob is the log-density of the
+    noise it drew, i.e. the PPO ratio of an unchanged policy is 1."""
+    import torch
+    import optimal_quad_control_rl_b200 as Q
+    gp, gy, sp = tracks["e2e"]
+    env = Q.Quadcopter3DGates(4096, gp, gy, sp, gates_ahead=1, reset_rng="device", seed=2)
+    env.disturbance_ranges = Q.training_disturbance_ranges()
+    ppo = Q.PPO("MlpPolicy", env, policy_kwargs=PK(), n_steps=64, batch_size=32768, n_epochs=2, gamma=0.999, seed=2)
+    assert ppo.evaluate == "device" and ppo.critic is not None
+    ppo.learn(iterations=3)  # move the weights off their initialisation (values of an untrained critic are ~0)
+    b = ppo.collect_rollouts()
+    T, n, d = 64, 4096, env.state_len
+    dev = {k: b[k].clone() for k in ("values", "log_probs", "weights")}
+    ppo.evaluate = "torch"
+    ppo._evaluate_buffer(b, T, n, d)
+    ppo.evaluate = "device"
+    assert torch.equal(dev["weights"], b["weights"])
+    scale = max(1.0, b["values"].abs().max().item())
+    ev = (dev["values"] - b["values"]).abs().max().item() / scale
+    em = (dev["values"] - b["values"]).abs().mean().item() / scale
+    el = (dev["log_probs"] - b["log_probs"]).abs().max().item()
+    print(f"device vs torch evaluation: values max {ev:.2e} mean {em:.2e} (scaled by {scale:.1f}), log-probs max {el:.2e}")
+    assert ev < 6e-2 and em < 6e-3 and el < 0.15  # BF16 operands through four layers (measured 2.6e-2 / 2.7e-2 at the maximum)
+    # the stored log-prob against the very mean the BF16 actor sampled around
+    mean = torch.empty((n, 4), device="cuda")
+    ppo.actor.forward(b["obs"][5], deterministic=True, mean_out=mean)
+    lp = ppo.policy.log_prob(mean, b["raw_actions"][5])
+    assert torch.allclose(lp, dev["log_probs"][5], atol=1e-5)
+    tr = ppo.train()
+    assert np.isfinite([tr["pg_loss"], tr["v_loss"], tr["approx_kl"]]).all() and tr["approx_kl"] < 0.1
+    env.close()
 
 
 def test_ppo_update_survives_degenerate_samples(tracks):
