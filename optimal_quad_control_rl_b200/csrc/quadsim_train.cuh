@@ -189,26 +189,63 @@ __global__ void __launch_bounds__(kPolRows, 1) ppo_grad_kernel(const __grid_cons
             umma_bf16(d, umma_desc(g + (uint32_t)j * 256u, 128, kSlab), umma_desc(h + (uint32_t)j * 256u, 128, kSlab), idesc, acc || j > 0);
     };
 
+    // The sample rows are gathered by index from the rollout buffers: random 100-byte reads whose DRAM latency (2 - 3 k
+    // cycles) used to stall the top of every tile and its loss stage (ncu: long_scoreboard 5.0 per issue).  The NEXT
+    // tile's row and loss inputs are requested while this tile computes and wait in registers (128 threads per SM:
+    // registers are free).
+    const bool vec_obs = (P.in_dim & 3) == 0 && (reinterpret_cast<uintptr_t>(P.obs) & 15u) == 0;
+    float xr[kTrMaxK1];                                   // this thread's observation row of the tile to come
+    float4 n_act = make_float4(0.f, 0.f, 0.f, 0.f);
+    float n_lp = 0.f, n_adv = 0.f, n_ret = 0.f, n_w = 0.f;
+    long long n_s = 0;
+    auto fetch_sample = [&](long long t) {
+        const long long r = t * kPolRows + tid;
+        const bool on = t < n_tiles && r < P.rows;
+        n_s = on ? (P.idx ? P.idx[r] : r) : 0;
+        const float *row = P.obs + n_s * P.in_dim;
+        if (vec_obs) {
+#pragma unroll
+            for (int q = 0; q < kTrMaxK1 / 4; ++q) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (on && 4 * q < P.in_dim) v = *reinterpret_cast<const float4 *>(row + 4 * q);
+                xr[4 * q] = v.x; xr[4 * q + 1] = v.y; xr[4 * q + 2] = v.z; xr[4 * q + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kTrMaxK1; ++k) xr[k] = (on && k < P.in_dim) ? row[k] : 0.0f;
+        }
+        n_w = on ? (P.weight ? P.weight[n_s] : 1.0f) : 0.0f;
+        if (on) {
+            if (net == 0) { n_act = *reinterpret_cast<const float4 *>(P.act + n_s * 4); n_lp = P.old_logp[n_s]; n_adv = P.adv[n_s]; }
+            else n_ret = P.ret[n_s];
+        }
+    };
+    fetch_sample(blockIdx.x >> 1);
+
     for (long long tile = blockIdx.x >> 1; tile < n_tiles; tile += ctas_per_net) {
         const long long r = tile * kPolRows + tid;
         const bool active = r < P.rows;
-        const long long s = active ? (P.idx ? P.idx[r] : r) : 0;
         // ---- X: this thread's observation row (sanitised like the torch path), BF16, constant 1 in column in_dim
+        const float4 a4 = n_act;
+        const float s_lp = n_lp, s_adv = n_adv, s_ret = n_ret, w = n_w;
         {
-            const float *row = P.obs + s * P.in_dim;
-            for (int c = 0; c < k1 / 8; ++c) {
-                float x[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int k = c * 8 + q;
-                    float v = (active && k < P.in_dim) ? row[k] : 0.0f;
-                    v = (v == v) ? fminf(fmaxf(v, -P.obs_limit), P.obs_limit) : 0.0f;
-                    x[q] = (k == P.in_dim) ? 1.0f : v;
+            for (int c = 0; c < kTrMaxK1 / 8; ++c) {
+                if (c < k1 / 8) {
+                    float x[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int k = c * 8 + q;
+                        float v = xr[k];
+                        v = (v == v) ? fminf(fmaxf(v, -P.obs_limit), P.obs_limit) : 0.0f;
+                        x[q] = (k == P.in_dim) ? 1.0f : v;
+                    }
+                    *reinterpret_cast<uint4 *>(s_x + c * kSlab + tid * 16) =
+                        make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
                 }
-                *reinterpret_cast<uint4 *>(s_x + c * kSlab + tid * 16) =
-                    make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
             }
         }
+        fetch_sample(tile + ctas_per_net);  // in flight for the whole tile
         // ---- forward: three hidden layers
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
@@ -235,10 +272,8 @@ __global__ void __launch_bounds__(kPolRows, 1) ppo_grad_kernel(const __grid_cons
             tmem_ld8(t_lane + kTmAcc, v);
             tmem_ld_wait();
             float g[4] = {0.f, 0.f, 0.f, 0.f};
-            const float w = active ? (P.weight ? P.weight[s] : 1.0f) : 0.0f;
-            if (w != 0.0f) {
+            if (active && w != 0.0f) {
                 if (net == 0) {
-                    const float4 a4 = *reinterpret_cast<const float4 *>(P.act + s * 4);
                     const float a[4] = {a4.x, a4.y, a4.z, a4.w};
                     float logp = 0.0f, z[4];
 #pragma unroll
@@ -247,12 +282,12 @@ __global__ void __launch_bounds__(kPolRows, 1) ppo_grad_kernel(const __grid_cons
                         z[k] = (ak - __uint_as_float(v[k])) * std_inv[k];
                         logp += -0.5f * z[k] * z[k] - log_std[k] - 0.9189385332046727f;
                     }
-                    float lr = logp - P.old_logp[s];
+                    float lr = logp - s_lp;
                     lr = (lr == lr) ? lr : 0.0f;
                     const bool lr_in = lr > -20.0f && lr < 20.0f;
                     lr = fminf(fmaxf(lr, -20.0f), 20.0f);
                     const float ratio = __expf(lr);
-                    const float ad = (P.adv[s] - adv_mean) * adv_rstd;
+                    const float ad = (s_adv - adv_mean) * adv_rstd;
                     const float s1 = ad * ratio, s2 = ad * fminf(fmaxf(ratio, 1.0f - P.clip_range), 1.0f + P.clip_range);
                     // d(-min(s1, s2))/d ratio: -adv where the unclipped term is the minimum (ties: both terms carry adv)
                     const float g_lp = (s1 <= s2 && lr_in) ? -ad * ratio * w : 0.0f;
@@ -266,7 +301,7 @@ __global__ void __launch_bounds__(kPolRows, 1) ppo_grad_kernel(const __grid_cons
                     st_clip += (fabsf(ratio - 1.0f) > P.clip_range) ? w : 0.0f;
                     st_kl += ((ratio - 1.0f) - lr) * w;
                 } else {
-                    const float d = __uint_as_float(v[0]) - P.ret[s];
+                    const float d = __uint_as_float(v[0]) - s_ret;
                     g[0] = 2.0f * P.vf_coef * d * w;
                     st_v += d * d * w;
                 }

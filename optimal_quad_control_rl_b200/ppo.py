@@ -293,12 +293,15 @@ class PPO:
         if fits:
             self.actor = MlpPolicy(*self._pi_arrays(), std=self.policy.log_std.detach().exp().cpu().numpy(), device=self.device,
                                    seed=0 if seed is None else int(seed), activation=act)
-        # values / old log-probs over the collected buffer: the same tcgen05 forward kernel (an actor and a critic instance
-        # that sanitise their inputs like the learner) instead of torch GEMMs -- 21 -> 3 ms per 8.4 M-sample buffer
+        # values / old log-probs over the collected buffer.  "torch" (default): float32 / TF32 forwards.  "device": the tcgen05
+        # forward kernel (an actor and a critic instance that sanitise their inputs like the learner), 23 -> 8 ms per
+        # 8.4 M-sample buffer -- but the critic then runs on BF16 operands (values off by up to 2.6 % of their range), and on
+        # the E2E env the one 130 s run with it plateaued at ep_rew_mean 115 - 137 instead of 145 - 160 (profiles/r2/ppo/):
+        # opt-in, for when the collect phase matters more than the last gates per episode.
         fits_vf = act is not None and vf == pi and fits
         if evaluate == "device" and not (fits_vf and self.rollout == "device"):
             raise ValueError("evaluate='device' needs rollout='device' and pi / vf networks of the same supported shape")
-        self.evaluate = "device" if (evaluate != "torch" and fits_vf and self.rollout == "device") else "torch"
+        self.evaluate = "device" if evaluate == "device" else "torch"
         self.eval_actor = self.critic = None
         if self.evaluate == "device":
             self.eval_actor = MlpPolicy(*self._pi_arrays(), device=self.device, activation=act, obs_limit=self.obs_limit)

@@ -52,8 +52,7 @@ def test_ppo_short_run_improves_reward(tracks):
     import optimal_quad_control_rl_b200 as Q
     gp, gy, sp = tracks["indi"]
     env = Q.Quadcopter3DGatesINDI(4096, gp, gy, sp, gates_ahead=1, reset_rng="device", seed=0)
-    ppo = Q.PPO("MlpPolicy", env, policy_kwargs=PK(), n_steps=128, batch_size=16384, n_epochs=4, gamma=0.999, seed=0,
-                evaluate="torch")
+    ppo = Q.PPO("MlpPolicy", env, policy_kwargs=PK(), n_steps=128, batch_size=16384, n_epochs=4, gamma=0.999, seed=0)
     b = ppo.collect_rollouts()
     with torch.no_grad():  # before any update: new log-prob == stored log-prob
         lp = ppo._log_prob(b["obs"][:4].reshape(-1, env.state_len), b["raw_actions"][:4].reshape(-1, 4))
@@ -73,7 +72,7 @@ def test_ppo_short_run_improves_reward(tracks):
 
 
 def test_buffer_evaluation_on_the_forward_kernel_matches_torch(tracks):
-    """`evaluate="device"` (default with the device rollout): values and old log-probs of the collected buffer come from two
+    """`evaluate="device"` (opt-in): values and old log-probs of the collected buffer come from two
     launches of the tcgen05 forward kernel instead of torch GEMMs.  Against the float32 torch pass on the same buffer: BF16
     operand rounding only; against the BF16 actor that sampled the actions: the stored log-prob is the log-density of the
     noise it drew, i.e. the PPO ratio of an unchanged policy is 1."""
@@ -82,7 +81,8 @@ def test_buffer_evaluation_on_the_forward_kernel_matches_torch(tracks):
     gp, gy, sp = tracks["e2e"]
     env = Q.Quadcopter3DGates(4096, gp, gy, sp, gates_ahead=1, reset_rng="device", seed=2)
     env.disturbance_ranges = Q.training_disturbance_ranges()
-    ppo = Q.PPO("MlpPolicy", env, policy_kwargs=PK(), n_steps=64, batch_size=32768, n_epochs=2, gamma=0.999, seed=2)
+    ppo = Q.PPO("MlpPolicy", env, policy_kwargs=PK(), n_steps=64, batch_size=32768, n_epochs=2, gamma=0.999, seed=2,
+                evaluate="device")
     assert ppo.evaluate == "device" and ppo.critic is not None
     ppo.learn(iterations=3)  # move the weights off their initialisation (values of an untrained critic are ~0)
     b = ppo.collect_rollouts()
