@@ -747,7 +747,9 @@ def run_ours(a):
                        "parallelism": f"env-sharded x{world}, no data-path collective" +
                                       (" + obs all-gather (%s)" % a.gather_obs if gather is not None else ""),
                        "done_rate": st["dones"] / max(1, st["env_steps"]) if not a.no_stats else None,
-                       "launch": timer.launch_mode, "cpu_affinity_cores": pinned_cpus},
+                       "launch": timer.launch_mode, "cpu_affinity_cores": pinned_cpus,
+                       # steps inside a graph that depend on their predecessor CTA by CTA instead of grid by grid
+                       "chained_launches": env.chained_launch_count},
             "replay_ms_per_step": replays,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,

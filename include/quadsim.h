@@ -191,6 +191,11 @@ void qs_host_free(void *p);
 int qs_algorithmic_bytes_per_env_step(int variant, int gates_ahead);
 /* number of kernel launches issued by this handle so far (bench.py's gpu_launches) */
 uint64_t qs_launch_count(const qs_env *env);
+/* how many of those were CHAINED step launches that skipped the grid-wide wait: consecutive full-range qs_step calls
+ * captured into one CUDA graph depend on each other CTA by CTA (CTA b steps the same tiles in every launch), so the next
+ * step's loads flow while this step's last tiles drain.  QS_CHAIN=0 in the environment turns it off.  Results are the
+ * same bit for bit (tests/test_gpu_chain.py).  No reference counterpart: the reference steps synchronously on the host. */
+uint64_t qs_chained_launch_count(const qs_env *env);
 /* geometry of the device-resident state, for zero-copy consumers.  Env i lives in block i/32 at lane i%32; block b
  * starts at base + b*block_bytes; inside a block every field is a 32-lane plane at offsets7[k]:
  *   0: (x,y,z,vx) float4   1: (vy,vz,phi,theta) float4   2: (psi,p,q,r) float4   3: (w1..w4) float4 | INDI: T_norm float

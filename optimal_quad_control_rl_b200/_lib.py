@@ -76,6 +76,7 @@ SIGNATURES = {
     "qs_host_free": (None, [_vp]),
     "qs_algorithmic_bytes_per_env_step": (C.c_int, [C.c_int, C.c_int]),
     "qs_launch_count": (C.c_uint64, [_vp]),
+    "qs_chained_launch_count": (C.c_uint64, [_vp]),
     "qs_get_state_layout": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "qs_policy_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "qs_policy_destroy": (C.c_int, [_vp]),

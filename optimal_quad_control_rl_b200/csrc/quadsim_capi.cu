@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <atomic>
 #include <string>
 #include <thread>
 #include <vector>
@@ -51,7 +52,7 @@ struct qs_env {
     uint8_t *h_done = nullptr, *h_flags = nullptr;
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
-    uint64_t launches = 0;
+    uint64_t launches = 0, chained_launches = 0;
     cudaStream_t copy_a = nullptr, copy_b = nullptr;  // host-buffer pipeline: upload+kernel / download
     cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr;
     int host_chunks = 4;   // measured on B200 + PCIe Gen5: 1 -> 4.67e8, 4 -> 5.13e8 env-steps/s at N = 2^20
@@ -59,11 +60,21 @@ struct qs_env {
     int l2_hints = 0;               // QS_L2_HINTS: state evict_last / streams evict_first in the step kernel
     double l2_keep_mb = 56.0;       // QS_L2_KEEP_MB: how much of the state to pin (one die's share of the 126 MB L2)
     bool pdl = true;                // programmatic dependent launch of consecutive steps
+    // Chained launches (QS_CHAIN, default on): consecutive full-range steps captured into ONE CUDA graph depend on each
+    // other CTA by CTA instead of grid by grid (StepParams::chain).  chain_tag / chain_capture say whether the previous
+    // early-triggering launch of this library was this env's chained step inside the same capture.
+    bool chain = true;
+    unsigned int *chain_dev = nullptr;
+    uint64_t chain_tag = 0;
+    unsigned long long chain_capture = 0;
     size_t step_smem = 0;
     std::string err;
 };
 
 static std::string g_create_error;
+// serial number of the last kernel this library launched with an early programmatic trigger (step, policy, rollout):
+// a chained step may skip griddepcontrol.wait only if nothing else of ours was launched since its predecessor
+static std::atomic<uint64_t> g_pdl_serial{0};
 
 #define QS_CHECK_ENV(e) \
     if (!(e)) return QS_ERR_ARG
@@ -91,6 +102,7 @@ int qs_algorithmic_bytes_per_env_step(int variant, int ga) {
 const char *qs_version(void) { return "quadsim-b200 0.1 (sm_100a)"; }
 const char *qs_last_error(const qs_env *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
 uint64_t qs_launch_count(const qs_env *e) { return e ? e->launches : 0; }
+uint64_t qs_chained_launch_count(const qs_env *e) { return e ? e->chained_launches : 0; }
 
 static void compute_track_tables(qs_env *e) {
     // Quadcopter3DGates.__init__ (`3D quad race.ipynb:309-319`): gate i expressed in the frame of gate i-1 (cyclic)
@@ -228,6 +240,7 @@ int qs_create(qs_env **out, int variant, int64_t num_envs, int n_gates, const fl
     // persistent step kernel: pipeline depth, shared memory, grid = SMs x resident CTAs
     if (const char *sv = getenv("QS_STAGES")) e->stages = atoi(sv) == 3 ? 3 : (atoi(sv) == 4 ? 4 : 2);
     if (const char *pv = getenv("QS_PDL")) e->pdl = atoi(pv) != 0;
+    if (const char *cv = getenv("QS_CHAIN")) e->chain = atoi(cv) != 0;
     // measured on B200 (profiles/r1/l2_pinning.md): INDI N = 2^20 41.9 -> 32.8 us/step, DRAM traffic per launch 177 ->
     // 136 MB; for E2E (96 MB of state + 122 MB of streams per step) the hints change neither traffic nor time
     e->l2_hints = variant == QS_INDI ? 1 : 0;
@@ -238,17 +251,20 @@ int qs_create(qs_env **out, int variant, int64_t num_envs, int n_gates, const fl
     if ((c = cudaFuncSetAttribute(step_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem)) != cudaSuccess)
         return bail(c, "cudaFuncSetAttribute(step smem)");
     int per_sm = 0, sms = 0;
-    if ((c = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_fn, qs::kStepThreads, e->step_smem)) != cudaSuccess)
+    if ((c = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_fn, qs::step_warps(variant) * 32, e->step_smem)) != cudaSuccess)
         return bail(c, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
     if ((c = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
         return bail(c, "cudaDeviceGetAttribute");
     if (per_sm < 1) { g_create_error = "step kernel does not fit on an SM (gates_ahead / n_gates too large)"; qs_destroy(e); return QS_ERR_ARG; }
     if (const char *cv = getenv("QS_CTAS_PER_SM")) { int v = atoi(cv); if (v >= 1 && v < per_sm) per_sm = v; }
     const long long tiles = (num_envs + qs::kBlock - 1) / qs::kBlock;
-    e->step_grid = (int)(tiles < (long long)sms * per_sm ? tiles : (long long)sms * per_sm);
+    const long long want = (tiles * (qs::kBlock / 32) + qs::step_warps(variant) - 1) / qs::step_warps(variant);  // one warp-tile per warp
+    e->step_grid = (int)(want < (long long)sms * per_sm ? want : (long long)sms * per_sm);
     // device-side totals: one slot per CTA, updated without atomics, summed on read
     if ((c = cudaMalloc(&e->stats_dev, sizeof(qs::Stats) * e->step_grid)) != cudaSuccess) return bail(c, "cudaMalloc");
     if ((c = cudaMemset(e->stats_dev, 0, sizeof(qs::Stats) * e->step_grid)) != cudaSuccess) return bail(c, "cudaMemset");
+    if ((c = cudaMalloc(&e->chain_dev, sizeof(unsigned int) * 2 * e->step_grid)) != cudaSuccess) return bail(c, "cudaMalloc");
+    if ((c = cudaMemset(e->chain_dev, 0, sizeof(unsigned int) * 2 * e->step_grid)) != cudaSuccess) return bail(c, "cudaMemset");
     *out = e;
     return QS_OK;
 }
@@ -258,7 +274,7 @@ int qs_destroy(qs_env *e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream); else cudaDeviceSynchronize();
     Planes &s = e->planes;
-    cudaFree(s.base); cudaFree(e->epoch_dev); cudaFree(e->track_dev); cudaFree(e->stats_dev); cudaFree(e->scratch);
+    cudaFree(s.base); cudaFree(e->epoch_dev); cudaFree(e->track_dev); cudaFree(e->stats_dev); cudaFree(e->chain_dev); cudaFree(e->scratch);
     cudaFree(e->h_act); cudaFree(e->h_obs); cudaFree(e->h_rew); cudaFree(e->h_done); cudaFree(e->h_flags);
     if (e->act_stage) cudaFreeHost(e->act_stage);
     cudaFree(e->info_dev);
@@ -517,12 +533,29 @@ static int launch_step(qs_env *e, long long t0, long long t1, int advance_epoch,
     StepParams &P = e->P;
     P.tile_begin = t0; P.tile_end = t1; P.advance_epoch = advance_epoch;
     const long long tiles = t1 - t0;
+    // chained launch: the whole env range on the env's own stream, nothing stored into peers.  It skips the grid-wide
+    // wait only inside a stream capture, behind another chained launch of this env in the SAME capture (a graph is
+    // replayed in contexts the host cannot see, so its first step always waits for everything before it).
+    const bool chainable = e->chain && e->chain_dev && pdl && advance_epoch && stream == e->stream && P.n_peers == 0 &&
+                           t0 == 0 && t1 == (e->n + qs::kBlock - 1) / qs::kBlock;
+    P.chain = chainable ? e->chain_dev : nullptr;
+    P.chain_wait = 0;
+    if (chainable) {
+        cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
+        unsigned long long cid = 0;
+        if (cudaStreamGetCaptureInfo(stream, &cst, &cid) != cudaSuccess) { cudaGetLastError(); cst = cudaStreamCaptureStatusNone; }
+        const bool capturing = cst == cudaStreamCaptureStatusActive;
+        if (capturing && cid == e->chain_capture && e->chain_tag != 0 && g_pdl_serial.load() == e->chain_tag) P.chain_wait = 1;
+        e->chain_capture = capturing ? cid : 0ull;
+    }
     // programmatic dependent launch: this grid's prologue may overlap the tail of the previous kernel on the
     // stream; the kernel itself waits (griddepcontrol.wait) before it touches simulator state
     void *args[] = {&P};
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(tiles < e->step_grid ? tiles : e->step_grid));
-    cfg.blockDim = dim3(qs::kStepThreads);
+    const int cta_warps = qs::step_warps(e->variant == QS_E2E ? qs::kE2E : qs::kINDI);
+    const long long want = (tiles * (qs::kBlock / 32) + cta_warps - 1) / cta_warps;  // CTAs that give every warp-tile a warp
+    cfg.gridDim = dim3((unsigned)(want < e->step_grid ? want : e->step_grid));
+    cfg.blockDim = dim3((unsigned)cta_warps * 32);
     cfg.dynamicSmemBytes = e->step_smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -531,7 +564,10 @@ static int launch_step(qs_env *e, long long t0, long long t1, int advance_epoch,
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     QS_CUDA(e, cudaLaunchKernelExC(&cfg, step_function(e), args));
+    const uint64_t tag = ++g_pdl_serial;
+    e->chain_tag = chainable ? tag : 0;
     e->launches++;
+    e->chained_launches += P.chain_wait ? 1 : 0;
     return QS_OK;
 }
 
@@ -936,6 +972,7 @@ static int policy_launch(qs_policy *p, const float *obs_dev, int64_t n, float *a
     cfg.numAttrs = 1;
     cudaError_t c = cudaLaunchKernelExC(&cfg, ts ? (const void *)qs::policy_kernel_ts : (const void *)qs::policy_kernel, args);
     if (c != cudaSuccess) { p->err = std::string("policy_kernel launch: ") + cudaGetErrorString(c); return QS_ERR_CUDA; }
+    ++g_pdl_serial;
     p->launches++;
     return QS_OK;
 }
@@ -1030,6 +1067,7 @@ int qs_rollout_fused(qs_env *e, qs_policy *p, int steps, float *obs_buf, float *
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     QS_CUDA(e, cudaLaunchKernelExC(&cfg, fn, args));
+    ++g_pdl_serial;
     e->launches++;
     p->launches++;
     return QS_OK;

@@ -83,6 +83,12 @@ struct StepParams {
     // a CUDA graph replaying the same launch draws fresh values; the last CTA of a launch to finish (epoch[1] counts
     // arrivals) advances it, i.e. after every CTA of this launch has read it and before the next launch may.
     unsigned long long *epoch;
+    // Chained launches (consecutive full-range steps of one env inside a CUDA graph): chain[2b] counts the launches CTA b
+    // has started, chain[2b+1] the ones it has finished.  CTA b steps the same tiles in every launch, so with
+    // chain_wait = 1 it waits for CTA b of the previous launch only (not for the whole grid, griddepcontrol.wait):
+    // the next step's loads flow while this step's last tiles drain.  NULL: classic launch.
+    unsigned int *chain;
+    int chain_wait;
     int n_gates, gates_ahead, obs_len;
     // 0: observations leave as float32 rows (N, obs_len), the reference's layout.  1: as BF16 in the on-device policy's
     // A-operand layout (pack_obs_row / pack_block_bytes below) -- `obs` and `peer_obs` then point to packed buffers
@@ -635,6 +641,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 // previous grid's memory before touching simulator state
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
@@ -692,6 +706,8 @@ __device__ __forceinline__ void st_hint(uint8_t *p, uint8_t v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.u8 [%0], %1, %2;" ::"l"(p), "r"((uint32_t)v), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // step_counts += 1, reward, gate logic and termination flags of one env (`3D quad race.ipynb:514-566`): `e` is the
@@ -732,14 +748,27 @@ __device__ __forceinline__ void reward_and_flags(const StepParams &P, const floa
 template <int V> struct Stage : Blk<V> {
     enum : int { ACT = Blk<V>::BYTES, BYTES = Blk<V>::BYTES + 512 };
 };
-constexpr int kBarBytes = 128;  // mbarriers live in the first 128 bytes of dynamic shared memory
-constexpr int kWarps = kBlock / 32;
+constexpr int kBarBytes = 256;  // mbarriers live in the first 256 bytes of dynamic shared memory
+// Worker warps per CTA of the step kernel.  A warp is an independent worker over 32-env warp-tiles, so the CTA size only
+// decides how many warps fit on an SM.  E2E (91 registers): 5 CTAs x 4 warps = 20 warps per SM.  Measured alternative
+// (QS_E2E_WARPS=7, 3 CTAs x 7 warps = 21 per SM, 148 x 21 workers would step 2^20 envs in 11 rounds instead of 12):
+// registers are allocated to a CTA in units of 4 warps, so 7-warp CTAs only fit with 80 registers per thread and the
+// tighter allocation costs more than the 21st warp gives back (57.8 vs 55.7 us per step at N = 2^20).
+// INDI (63 registers): 8 CTAs x 4 warps = 32 warps per SM.
+#ifndef QS_E2E_WARPS
+#define QS_E2E_WARPS 4
+#endif
+template <int V> struct StepCta {
+    enum : int { WARPS = (V == kE2E ? QS_E2E_WARPS : 4), THREADS = WARPS * 32,
+                 MIN_CTAS = (V == kE2E ? (QS_E2E_WARPS == 7 ? 3 : QS_E2E_WARPS == 4 ? 5 : 1) : 8) };
+};
+__host__ __device__ constexpr int step_warps(int variant) { return variant == kE2E ? (int)StepCta<kE2E>::WARPS : (int)StepCta<kINDI>::WARPS; }
 
 // a warp's observation staging slice: its 32 float32 rows, and never less than the largest packed BF16 block (2 KB)
 __host__ __device__ constexpr int step_slice_floats(int obs_len) { return 32 * obs_len > 512 ? 32 * obs_len : 512; }
 __host__ __device__ constexpr size_t step_smem_bytes(int variant, int stages, int obs_len, int n_gates) {
-    return kBarBytes + (size_t)stages * kWarps * (variant == kE2E ? (int)Stage<kE2E>::BYTES : (int)Stage<kINDI>::BYTES) +
-           (size_t)kWarps * step_slice_floats(obs_len) * 4 + (size_t)n_gates * kTrackRow * 4;
+    return kBarBytes + (size_t)stages * step_warps(variant) * (variant == kE2E ? (int)Stage<kE2E>::BYTES : (int)Stage<kINDI>::BYTES) +
+           (size_t)step_warps(variant) * step_slice_floats(obs_len) * 4 + (size_t)n_gates * kTrackRow * 4;
 }
 
 // lane 0 of a warp: fill one of the warp's stages with the 32 envs starting at `first`
@@ -766,11 +795,11 @@ __device__ __forceinline__ void issue_warp_tile(const StepParams &P, unsigned ch
 // There is no block barrier anywhere in the loop, so the warps of an SM drift apart: while one computes, others
 // load or store.  Observations leave through the warp's slice of the staging tile as one TMA bulk store (32 rows
 // of a row-major (N,D) array are contiguous).  kHints: the L2 residency policies (see l2_policy_*) are compiled in.
-constexpr int kStepThreads = kBlock;
-
 template <int V, int kStages, bool kHints>
-__global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel(const __grid_constant__ StepParams P) {
+__global__ void __launch_bounds__(StepCta<V>::THREADS, StepCta<V>::MIN_CTAS) step_kernel(const __grid_constant__ StepParams P) {
     using S = Stage<V>;
+    constexpr int kWarps = StepCta<V>::WARPS, kStepThreads = StepCta<V>::THREADS;
+    static_assert(kWarps * kStages * 8 <= kBarBytes, "mbarriers do not fit");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     // INDI: the shuffle tells the compiler that `warp` is warp-uniform, so everything derived from it (stage, barrier,
@@ -784,8 +813,11 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
     float *s_obs = reinterpret_cast<float *>(smem_raw + kBarBytes + kWarps * kStages * S::BYTES);
     const int slice = step_slice_floats(P.obs_len);
     float *s_track = s_obs + kWarps * slice;
-    const long long n_tiles = P.tile_end;
-    const long long tile0 = P.tile_begin + blockIdx.x;
+    // work unit = a 32-env warp-tile (one state block); worker = a warp; the launch covers the 128-env tiles
+    // [tile_begin, tile_end) = warp-tiles [4*tile_begin, 4*tile_end), dealt round-robin to the grid's warps
+    const long long n_tiles = P.tile_end * (kBlock / 32);
+    const long long tile0 = P.tile_begin * (kBlock / 32) + (long long)blockIdx.x * kWarps + warp;
+    const long long stride = (long long)gridDim.x * kWarps;
 
     if (lane == 0) {
 #pragma unroll
@@ -797,13 +829,42 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
     __syncthreads();  // barrier init and track table visible to everyone
     // Everything above touched only launch constants.  From here on we read and write simulator state that the
     // previous step's grid may still be producing (programmatic dependent launch).
-    pdl_launch_dependents();
-    pdl_wait();
+    unsigned long long launch_epoch;  // the RNG epoch of this launch (the same for every CTA)
+    unsigned chain_seq = 0;           // thread 0: how many chained launches this CTA slot had started before this one
+    if (P.chain == nullptr) {
+        pdl_launch_dependents();
+        pdl_wait();
+        launch_epoch = load_epoch(P.epoch);  // advanced by the last CTA of this launch to FINISH (epoch_arrive)
+    } else {
+        // Chained launch.  Order matters: the epoch is read and advanced (by the last CTA to arrive) BEFORE this CTA
+        // lets the next launch start, so every CTA of the next launch reads epoch + 1 although this launch still runs.
+        __shared__ unsigned long long s_epoch;
+        if (!P.chain_wait) pdl_wait();  // the previous kernel is not a chained step of this env: wait for all of it
+        if (tid == 0) {
+            const unsigned long long ep = load_epoch(P.epoch);
+            s_epoch = ep;
+            if (atomicAdd(P.epoch + 1, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+                *reinterpret_cast<volatile unsigned long long *>(P.epoch + 1) = 0ull;
+                *reinterpret_cast<volatile unsigned long long *>(P.epoch) = ep + 1ull;
+            }
+            chain_seq = atomicAdd(P.chain + 2 * blockIdx.x, 1u);
+            __threadfence();
+        }
+        __syncthreads();
+        launch_epoch = s_epoch;
+        pdl_launch_dependents();
+        if (P.chain_wait) {  // CTA b of the previous launch wrote the state blocks this CTA is about to load
+            if (tid == 0)
+                while (ld_acquire_gpu(P.chain + 2 * blockIdx.x + 1) != chain_seq) __nanosleep(40);
+            __syncthreads();
+            if (lane == 0) fence_proxy_async_all();  // its generic-proxy stores, before this warp's bulk (async-proxy) loads
+        }
+    }
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) {
-            const long long t = tile0 + (long long)s * gridDim.x;
-            if (t < n_tiles) issue_warp_tile<V, kHints>(P, stages + s * S::BYTES, &full[s], t * kBlock + warp * 32, pol_keep, pol_stream);
+            const long long t = tile0 + (long long)s * stride;
+            if (t < n_tiles) issue_warp_tile<V, kHints>(P, stages + s * S::BYTES, &full[s], t * 32, pol_keep, pol_stream);
         }
     }
 
@@ -816,11 +877,11 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
     float *const my_obs = warp_obs + lane * P.obs_len;
     bool obs_in_flight = false;  // warp-uniform: a bulk store of this warp's observation slice may still be reading it
     int it = 0;
-    for (long long tile = tile0; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (long long tile = tile0; tile < n_tiles; tile += stride, ++it) {
         const int stage = it % kStages;
         unsigned char *st = stages + stage * S::BYTES;
-        const long long base = tile * kBlock;
-        const long long env = base + tid;
+        const long long base = tile * 32;  // first env of this warp-tile
+        const long long env = base + lane;
         const bool active = env < P.n;
         mbar_wait(&full[stage], (uint32_t)(it / kStages) & 1u);
 
@@ -847,8 +908,8 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
         uint32_t tg = meta >> 24, sc = meta & kStepMask;
         __syncwarp();  // the warp's inputs are in registers: refill the stage with the tile kStages ahead
         if (lane == 0) {
-            const long long nt = tile + (long long)kStages * gridDim.x;
-            if (nt < n_tiles) issue_warp_tile<V, kHints>(P, st, &full[stage], nt * kBlock + warp * 32, pol_keep, pol_stream);
+            const long long nt = tile + (long long)kStages * stride;
+            if (nt < n_tiles) issue_warp_tile<V, kHints>(P, st, &full[stage], nt * 32, pol_keep, pol_stream);
         }
 
 #ifdef QS_EXP_NOCOMPUTE  // experiment only: the memory pipeline alone (same loads and stores, no arithmetic)
@@ -873,7 +934,7 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
                 if (lane == 0 && obs_in_flight) bulk_store_wait_read();
                 obs_in_flight = false;
                 __syncwarp();
-                draw_reset_warp<V>(P, base + warp * 32, need, reinterpret_cast<uint4 *>(warp_obs), n, load_epoch(P.epoch));
+                draw_reset_warp<V>(P, base, need, reinterpret_cast<uint4 *>(warp_obs), n, launch_epoch);
             }
             if (need) {
                 tg = 0; sc = 0;
@@ -884,7 +945,7 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
         } else if (P.mode == kModePause) {
             write_world = false;
         }
-        unsigned char *const gblk = P.s.base + (tile * kWarps + warp) * (long long)Blk<V>::BYTES;  // this warp's block
+        unsigned char *const gblk = P.s.base + tile * (long long)Blk<V>::BYTES;  // this warp's block
         const uint8_t dn8 = (P.mode == kModePause) ? (uint8_t)0 : (uint8_t)(dn ? 1 : 0);
         if (!kHints) {
             if (active) {
@@ -905,7 +966,7 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
                 reinterpret_cast<float2 *>(gblk + S::DB)[lane] = make_float2(n.dist[3], n.dist[4]);
             }
         } else {  // the same stores with L2 priorities: state lines stay, result streams leave first
-            const uint64_t pol_state = (tile * kWarps + warp) < P.keep_blocks ? pol_keep : pol_stream;
+            const uint64_t pol_state = tile < P.keep_blocks ? pol_keep : pol_stream;
             if (active) {
                 st_hint(reinterpret_cast<uint32_t *>(gblk + S::META) + lane, (tg << 24) | sc, pol_state);
                 st_hint(P.rew + env, reward, pol_stream);
@@ -948,7 +1009,7 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
-                    const long long b32 = tile * kWarps + warp;  // 32-env block index within this launch's env range
+                    const long long b32 = tile;  // 32-env block index within this launch's env range
                     const uint32_t pkb = (uint32_t)pack_block_bytes(P.obs_len);
                     unsigned char *pk = reinterpret_cast<unsigned char *>(P.obs) + b32 * (long long)pkb;
                     if (kHints) bulk_store_hint(pk, warp_obs, pkb, pol_stream);
@@ -965,9 +1026,9 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
                 }
                 continue;
             }
-            const long long rem = P.n - (base + warp * 32);
+            const long long rem = P.n - base;
             const int rows = rem < 32 ? (rem < 0 ? 0 : (int)rem) : 32;
-            float *dst = P.obs + (base + warp * 32) * P.obs_len;
+            float *dst = P.obs + base * P.obs_len;
             const uint32_t bytes = (uint32_t)rows * (uint32_t)P.obs_len * 4u;
             // (peer destinations: base pointers are 16-byte aligned and qs_set_obs_peers rejects a row offset that
             // would misalign them, so the local test covers every destination of the tile)
@@ -980,7 +1041,7 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
                     else bulk_store(dst, warp_obs, bytes);
 #pragma unroll 1
                     for (int p = 0; p < P.n_peers; ++p)  // NVLink: the tile leaves for every peer while the next one is computed
-                        bulk_store(P.peer_obs[p] + (P.peer_row_offset + base + warp * 32) * P.obs_len, warp_obs, bytes);
+                        bulk_store(P.peer_obs[p] + (P.peer_row_offset + base) * P.obs_len, warp_obs, bytes);
                 }
                 obs_in_flight = true;
             } else {
@@ -989,7 +1050,7 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
                 for (int i = lane; i < rows * P.obs_len; i += 32) dst[i] = warp_obs[i];
 #pragma unroll 1
                 for (int p = 0; p < P.n_peers; ++p) {
-                    float *pd = P.peer_obs[p] + (P.peer_row_offset + base + warp * 32) * P.obs_len;
+                    float *pd = P.peer_obs[p] + (P.peer_row_offset + base) * P.obs_len;
 #pragma unroll 1
                     for (int i = lane; i < rows * P.obs_len; i += 32) pd[i] = warp_obs[i];
                 }
@@ -1002,14 +1063,17 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
             c_gc += (fl & F_COLLISION) != 0; c_gr += (fl & F_GROUND) != 0; c_ob += (fl & F_OOB) != 0;
         }
     }
-    if (lane == 0 && write_obs_tile) bulk_store_wait_read();  // shared memory must outlive the last bulk read
-    __syncthreads();  // every warp of the CTA is past its last reset draw
-    if (tid == 0 && P.advance_epoch) epoch_arrive(P);
+    if (lane == 0 && write_obs_tile) {
+        if (P.chain) bulk_store_wait_all();  // chained: the rows have LANDED before the next launch's CTA may rewrite them
+        else bulk_store_wait_read();         // shared memory must outlive the last bulk read
+    }
+    __syncthreads();  // every warp of the CTA is past its last reset draw (and, chained, its last store)
+    if (tid == 0 && P.advance_epoch && !P.chain) epoch_arrive(P);
 
     if (P.stats) {  // warp-shuffle reduction, then ONE plain read-modify-write per CTA on the CTA's own slot:
                     // no atomics (740-1184 CTAs hammering one address cost 1-4 us per launch), summed by qs_get_stats
-        __shared__ float s_red_f[kBlock / 32];
-        __shared__ unsigned s_red_u[kBlock / 32][7];
+        __shared__ float s_red_f[kWarps];
+        __shared__ unsigned s_red_u[kWarps][7];
         const unsigned full_mask = 0xffffffffu;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) reward_acc += __shfl_xor_sync(full_mask, reward_acc, o);
@@ -1028,7 +1092,7 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
             float r = 0.0f;
             unsigned c[7] = {0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-            for (int w = 0; w < kBlock / 32; ++w) {
+            for (int w = 0; w < kWarps; ++w) {
                 r += s_red_f[w];
 #pragma unroll
                 for (int k = 0; k < 7; ++k) c[k] += s_red_u[w][k];
@@ -1040,6 +1104,10 @@ __global__ void __launch_bounds__(kStepThreads, (V == kE2E ? 5 : 8)) step_kernel
                 st->gate_collisions += c[4]; st->ground_collisions += c[5]; st->out_of_bounds += c[6];
             }
         }
+    }
+    if (tid == 0 && P.chain) {  // chained: hand this CTA's tiles (and its stats slot) to CTA b of the next launch
+        __threadfence();
+        st_release_gpu(P.chain + 2 * blockIdx.x + 1, chain_seq + 1u);
     }
 }
 

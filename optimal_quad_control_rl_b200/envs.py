@@ -543,6 +543,11 @@ class _QuadGatesBase(_VecEnvBase):
     def launch_count(self):
         return int(self._lib.qs_launch_count(self._h))
 
+    @property
+    def chained_launch_count(self):
+        """Step launches that depended on their predecessor CTA by CTA (consecutive steps inside one CUDA graph)."""
+        return int(self._lib.qs_chained_launch_count(self._h))
+
     # ------------------------------------------------------------------------------------------ VecEnv plumbing (`:597-620`)
     def seed(self, seed=None):
         pass  # the reference's seed() is a no-op: seeding is np.random.seed by the caller (`:600-601`)

@@ -1,0 +1,93 @@
+"""Chained step launches (StepParams::chain): consecutive steps captured into one CUDA graph depend on each other CTA
+by CTA instead of grid by grid.  Whatever the overlap, the results must be the ones of the classic launch order, bit
+for bit: same states, observations, rewards, flags, device RNG draws and reward statistics."""
+import numpy as np
+import pytest
+
+from test_gpu_parity import VARIANTS, make_env
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(variant, n, tracks, chain, graph_steps, replays, eager_between, monkeypatch):
+    import torch
+    monkeypatch.setenv("QS_CHAIN", "1" if chain else "0")
+    env = make_env(variant, n, tracks, reset_rng="device", seed=5, obs_buffers=2)
+    if variant == "e2e":
+        import optimal_quad_control_rl_b200 as Q
+        env.disturbance_ranges = Q.training_disturbance_ranges()
+    env.max_steps = 7  # time-outs in every replay: the fused reset draws (keyed by the launch epoch) run all the time
+    env.enable_stats()
+    env.reset_tensor()
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    acts = [torch.rand((n, 4), device="cuda", generator=gen) * 2 - 1 for _ in range(graph_steps)]
+    outs = []
+    if graph_steps:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            env.step_tensor(acts[0])  # warm-up launch outside the capture
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for a in acts:
+                last = env.step_tensor(a)
+        for r in range(replays):
+            g.replay()
+            got = [t.clone() for t in last]  # before the eager step recycles the ring slot
+            if eager_between:
+                env.step_tensor(acts[r % graph_steps])  # an eager launch between two replays
+            torch.cuda.synchronize()
+            outs.append(got + [torch.from_numpy(env.world_states.copy())])
+    torch.cuda.synchronize()
+    # every captured step but the first of the graph skipped the grid-wide wait -- or none did with QS_CHAIN=0
+    assert env.chained_launch_count == ((graph_steps - 1) if chain else 0)
+    st = env.stats()
+    final = (env.world_states.copy(), env.target_gates.copy(), env.step_counts.copy())
+    env.close()
+    return outs, final, st
+
+
+def _eager_reference(variant, n, tracks, graph_steps, replays, eager_between, monkeypatch):
+    """The same call sequence, one classic launch per step (no graph, chaining compiled out of the decision)."""
+    import torch
+    monkeypatch.setenv("QS_CHAIN", "0")
+    env = make_env(variant, n, tracks, reset_rng="device", seed=5, obs_buffers=2)
+    if variant == "e2e":
+        import optimal_quad_control_rl_b200 as Q
+        env.disturbance_ranges = Q.training_disturbance_ranges()
+    env.max_steps = 7
+    env.enable_stats()
+    env.reset_tensor()
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    acts = [torch.rand((n, 4), device="cuda", generator=gen) * 2 - 1 for _ in range(graph_steps)]
+    outs = []
+    env.step_tensor(acts[0])
+    for r in range(replays):
+        for a in acts:
+            last = env.step_tensor(a)
+        last = [t.clone() for t in last]
+        if eager_between:
+            env.step_tensor(acts[r % graph_steps])
+        torch.cuda.synchronize()
+        outs.append(last + [torch.from_numpy(env.world_states.copy())])
+    final = (env.world_states.copy(), env.target_gates.copy(), env.step_counts.copy())
+    assert env.chained_launch_count == 0
+    st = env.stats()
+    env.close()
+    return outs, final, st
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("n,eager_between", [(300_000, False), (4096, False), (1000, True), (1 << 20, False)])
+def test_chained_graph_replays_equal_classic_launches(variant, n, eager_between, tracks, monkeypatch):
+    steps, replays = 6, 4
+    ref_outs, ref_final, ref_st = _eager_reference(variant, n, tracks, steps, replays, eager_between, monkeypatch)
+    for chain in (True, False):  # the graph with chained launches, and the same graph with classic ones
+        outs, final, st = _run(variant, n, tracks, chain, steps, replays, eager_between, monkeypatch)
+        for r, (a, b) in enumerate(zip(outs, ref_outs)):
+            for k, (x, y) in enumerate(zip(a, b)):
+                assert np.array_equal(x.cpu().numpy(), y.cpu().numpy()), (chain, "replay", r, "tensor", k)
+        for x, y in zip(final, ref_final):
+            np.testing.assert_array_equal(x, y)
+        assert st == ref_st
