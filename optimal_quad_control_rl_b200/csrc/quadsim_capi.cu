@@ -57,6 +57,7 @@ struct qs_env {
     cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr;
     int host_chunks = 4;   // measured on B200 + PCIe Gen5: 1 -> 4.67e8, 4 -> 5.13e8 env-steps/s at N = 2^20
     int stages = 2, step_grid = 0;  // pipeline depth and persistent grid of the step kernel
+    int stats_slots = 0;            // statistics / chain-ticket slots: one per CTA of the larger of the two step grids
     int l2_hints = 0;               // QS_L2_HINTS: state evict_last / streams evict_first in the step kernel
     double l2_keep_mb = 56.0;       // QS_L2_KEEP_MB: how much of the state to pin (one die's share of the 126 MB L2)
     bool pdl = true;                // programmatic dependent launch of consecutive steps
@@ -67,6 +68,12 @@ struct qs_env {
     unsigned int *chain_dev = nullptr;
     uint64_t chain_tag = 0;
     unsigned long long chain_capture = 0;
+    bool chain_x2 = false;          // kernel of the last chainable launch (a chain never spans two kernels)
+    // E2E with two envs per thread (step_kernel_x2; QS_STEP_X2=0 turns it off): used when every warp of its grid gets
+    // at least two warp-tiles and the launch needs none of the features only step_kernel has (see launch_step)
+    bool x2 = false;
+    int step_grid_x2 = 0;
+    size_t step_smem_x2 = 0;
     size_t step_smem = 0;
     std::string err;
 };
@@ -173,8 +180,8 @@ static void refresh_params(qs_env *e) {
 #define QS_STEP_FN(V, H) \
     (e->stages == 3 ? (const void *)qs::step_kernel<V, 3, H> : e->stages == 4 ? (const void *)qs::step_kernel<V, 4, H> : (const void *)qs::step_kernel<V, 2, H>)
 static const void *step_function(const qs_env *e) {
-    if (e->variant == QS_E2E) return e->l2_hints ? QS_STEP_FN(qs::kE2E, true) : QS_STEP_FN(qs::kE2E, false);
-    return e->l2_hints ? QS_STEP_FN(qs::kINDI, true) : QS_STEP_FN(qs::kINDI, false);
+    if (e->variant == QS_E2E) return e->l2_hints == 1 ? QS_STEP_FN(qs::kE2E, true) : QS_STEP_FN(qs::kE2E, false);
+    return e->l2_hints == 1 ? QS_STEP_FN(qs::kINDI, true) : QS_STEP_FN(qs::kINDI, false);
 }
 #undef QS_STEP_FN
 
@@ -242,8 +249,9 @@ int qs_create(qs_env **out, int variant, int64_t num_envs, int n_gates, const fl
     if (const char *pv = getenv("QS_PDL")) e->pdl = atoi(pv) != 0;
     if (const char *cv = getenv("QS_CHAIN")) e->chain = atoi(cv) != 0;
     // measured on B200 (profiles/r1/l2_pinning.md): INDI N = 2^20 41.9 -> 32.8 us/step, DRAM traffic per launch 177 ->
-    // 136 MB; for E2E (96 MB of state + 122 MB of streams per step) the hints change neither traffic nor time
-    e->l2_hints = variant == QS_INDI ? 1 : 0;
+    // 136 MB.  E2E (96 MB of state + 122 MB of streams per step): 272 -> 258 MB and, with chained launches, 57.4 -> 56.6 us
+    // (1 - 2 %, keep 40 - 72 MB alike; nothing without chaining, nothing at N = 262144: profiles/r2/step_kernel_ablation.md)
+    e->l2_hints = 1;
     if (const char *hv = getenv("QS_L2_HINTS")) e->l2_hints = atoi(hv) != 0;
     if (const char *kv = getenv("QS_L2_KEEP_MB")) { double v = atof(kv); if (v >= 0.0 && v <= 4096.0) e->l2_keep_mb = v; }
     const void *step_fn = step_function(e);
@@ -260,11 +268,27 @@ int qs_create(qs_env **out, int variant, int64_t num_envs, int n_gates, const fl
     const long long tiles = (num_envs + qs::kBlock - 1) / qs::kBlock;
     const long long want = (tiles * (qs::kBlock / 32) + qs::step_warps(variant) - 1) / qs::step_warps(variant);  // one warp-tile per warp
     e->step_grid = (int)(want < (long long)sms * per_sm ? want : (long long)sms * per_sm);
+    // opt-in (QS_STEP_X2=1): bit-identical to step_kernel<e2e> but measured slower on B200 (75 vs 57 us per step at
+    // N = 2^20: its 2x larger loop body does not stay in the instruction cache), see profiles/r2/step_kernel_ablation.md
+    if (variant == QS_E2E && e->l2_hints == 0 && qs::step_x2_supports(e->obs_len))
+        if (const char *xv = getenv("QS_STEP_X2")) e->x2 = atoi(xv) != 0;
+    if (e->x2) {
+        e->step_smem_x2 = qs::step_x2_smem_bytes(n_gates);
+        int per_sm2 = 0;
+        if ((c = cudaFuncSetAttribute((const void *)qs::step_kernel_x2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->step_smem_x2)) != cudaSuccess ||
+            (c = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, (const void *)qs::step_kernel_x2, qs::kX2Warps * 32, e->step_smem_x2)) != cudaSuccess)
+            return bail(c, "step_kernel_x2 setup");
+        if (const char *cv = getenv("QS_X2_CTAS_PER_SM")) { int v = atoi(cv); if (v >= 1 && v < per_sm2) per_sm2 = v; }
+        e->step_grid_x2 = sms * per_sm2;
+        if (per_sm2 < 1) e->x2 = false;
+    }
     // device-side totals: one slot per CTA, updated without atomics, summed on read
-    if ((c = cudaMalloc(&e->stats_dev, sizeof(qs::Stats) * e->step_grid)) != cudaSuccess) return bail(c, "cudaMalloc");
-    if ((c = cudaMemset(e->stats_dev, 0, sizeof(qs::Stats) * e->step_grid)) != cudaSuccess) return bail(c, "cudaMemset");
-    if ((c = cudaMalloc(&e->chain_dev, sizeof(unsigned int) * 2 * e->step_grid)) != cudaSuccess) return bail(c, "cudaMalloc");
-    if ((c = cudaMemset(e->chain_dev, 0, sizeof(unsigned int) * 2 * e->step_grid)) != cudaSuccess) return bail(c, "cudaMemset");
+    const int slots = e->step_grid > e->step_grid_x2 ? e->step_grid : e->step_grid_x2;
+    if ((c = cudaMalloc(&e->stats_dev, sizeof(qs::Stats) * slots)) != cudaSuccess) return bail(c, "cudaMalloc");
+    if ((c = cudaMemset(e->stats_dev, 0, sizeof(qs::Stats) * slots)) != cudaSuccess) return bail(c, "cudaMemset");
+    e->stats_slots = slots;
+    if ((c = cudaMalloc(&e->chain_dev, sizeof(unsigned int) * 2 * slots)) != cudaSuccess) return bail(c, "cudaMalloc");
+    if ((c = cudaMemset(e->chain_dev, 0, sizeof(unsigned int) * 2 * slots)) != cudaSuccess) return bail(c, "cudaMemset");
     *out = e;
     return QS_OK;
 }
@@ -390,7 +414,7 @@ int qs_get_stats(qs_env *e, qs_stats *out, int reset) {
     QS_CHECK_ENV(e);
     if (!out) return fail(e, QS_ERR_ARG, "qs_get_stats: NULL");
     QS_CUDA(e, cudaSetDevice(e->device));
-    std::vector<qs_stats> slots((size_t)e->step_grid);
+    std::vector<qs_stats> slots((size_t)e->stats_slots);
     const size_t bytes = sizeof(qs_stats) * slots.size();
     QS_CUDA(e, cudaMemcpyAsync(slots.data(), e->stats_dev, bytes, cudaMemcpyDeviceToHost, e->stream));
     if (reset) QS_CUDA(e, cudaMemsetAsync(e->stats_dev, 0, bytes, e->stream));
@@ -540,13 +564,18 @@ static int launch_step(qs_env *e, long long t0, long long t1, int advance_epoch,
                            t0 == 0 && t1 == (e->n + qs::kBlock - 1) / qs::kBlock;
     P.chain = chainable ? e->chain_dev : nullptr;
     P.chain_wait = 0;
+    // two envs per thread (E2E): float32 rows, nothing stored into peers, and enough work for two warp-tiles per warp
+    const bool x2 = e->x2 && !P.obs_packed && P.n_peers == 0 && P.l2_hints == 0 &&
+                    tiles * (qs::kBlock / 32) >= 2LL * e->step_grid_x2 * qs::kX2Warps;
     if (chainable) {
         cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
         unsigned long long cid = 0;
         if (cudaStreamGetCaptureInfo(stream, &cst, &cid) != cudaSuccess) { cudaGetLastError(); cst = cudaStreamCaptureStatusNone; }
         const bool capturing = cst == cudaStreamCaptureStatusActive;
-        if (capturing && cid == e->chain_capture && e->chain_tag != 0 && g_pdl_serial.load() == e->chain_tag) P.chain_wait = 1;
+        if (capturing && cid == e->chain_capture && e->chain_tag != 0 && g_pdl_serial.load() == e->chain_tag && e->chain_x2 == x2)
+            P.chain_wait = 1;
         e->chain_capture = capturing ? cid : 0ull;
+        e->chain_x2 = x2;
     }
     // programmatic dependent launch: this grid's prologue may overlap the tail of the previous kernel on the
     // stream; the kernel itself waits (griddepcontrol.wait) before it touches simulator state
@@ -557,13 +586,18 @@ static int launch_step(qs_env *e, long long t0, long long t1, int advance_epoch,
     cfg.gridDim = dim3((unsigned)(want < e->step_grid ? want : e->step_grid));
     cfg.blockDim = dim3((unsigned)cta_warps * 32);
     cfg.dynamicSmemBytes = e->step_smem;
+    if (x2) {
+        cfg.gridDim = dim3((unsigned)e->step_grid_x2);
+        cfg.blockDim = dim3((unsigned)qs::kX2Warps * 32);
+        cfg.dynamicSmemBytes = e->step_smem_x2;
+    }
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    QS_CUDA(e, cudaLaunchKernelExC(&cfg, step_function(e), args));
+    QS_CUDA(e, cudaLaunchKernelExC(&cfg, x2 ? (const void *)qs::step_kernel_x2 : step_function(e), args));
     const uint64_t tag = ++g_pdl_serial;
     e->chain_tag = chainable ? tag : 0;
     e->launches++;

@@ -497,6 +497,79 @@ __device__ __forceinline__ void residual_mlp(const StepParams &P, const float (&
     unpack2(a2, lo, hi); mom[2] = add_rn(lo, hi);
 }
 
+// The same two nets for TWO envs of one thread (step_kernel_x2): every weight pair is fetched once and used for both,
+// which halves the LDCU / LDC traffic per env; per env the operations and their order are exactly residual_mlp's.
+__device__ __forceinline__ void residual_mlp2(const StepParams &P, const float (&xa)[10], const float (&xb)[10], float &thrust_a,
+                                              float (&mom_a)[3], float &thrust_b, float (&mom_b)[3]) {
+    constexpr int C = QS_MLP_CHAINS;
+    f32x2 xxa[10], xxb[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) { xxa[k] = pack2(xa[k], xa[k]); xxb[k] = pack2(xb[k], xb[k]); }
+    f32x2 ata = pack2(P.b2[0], 0.0f), atb = ata;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2 * C) {
+        f32x2 ha[C], hb[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) ha[c] = hb[c] = pack2(P.bt1[j + 2 * c], P.bt1[j + 2 * c + 1]);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const f32x2 w = pack2(P.wt1[k * 32 + j + 2 * c], P.wt1[k * 32 + j + 2 * c + 1]);
+                ha[c] = fma2(w, xxa[k], ha[c]);
+                hb[c] = fma2(w, xxb[k], hb[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const f32x2 w = pack2(P.wt2[j + 2 * c], P.wt2[j + 2 * c + 1]);
+            float h0, h1;
+            unpack2(ha[c], h0, h1);
+            ata = fma2(pack2(fmaxf(h0, 0.0f), fmaxf(h1, 0.0f)), w, ata);
+            unpack2(hb[c], h0, h1);
+            atb = fma2(pack2(fmaxf(h0, 0.0f), fmaxf(h1, 0.0f)), w, atb);
+        }
+    }
+    float lo, hi;
+    unpack2(ata, lo, hi); thrust_a = add_rn(lo, hi);
+    unpack2(atb, lo, hi); thrust_b = add_rn(lo, hi);
+    f32x2 a0 = pack2(P.b2[1], 0.0f), a1 = pack2(P.b2[2], 0.0f), a2 = pack2(P.b2[3], 0.0f), b0 = a0, b1 = a1, b2 = a2;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2 * C) {
+        f32x2 ha[C], hb[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) ha[c] = hb[c] = pack2(P.bm1[j + 2 * c], P.bm1[j + 2 * c + 1]);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const f32x2 w = pack2(P.wm1[k * 32 + j + 2 * c], P.wm1[k * 32 + j + 2 * c + 1]);
+                ha[c] = fma2(w, xxa[k], ha[c]);
+                hb[c] = fma2(w, xxb[k], hb[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const f32x2 w0 = pack2(P.wm2[j + 2 * c], P.wm2[j + 2 * c + 1]);
+            const f32x2 w1 = pack2(P.wm2[32 + j + 2 * c], P.wm2[32 + j + 2 * c + 1]);
+            const f32x2 w2 = pack2(P.wm2[64 + j + 2 * c], P.wm2[64 + j + 2 * c + 1]);
+            float h0, h1;
+            unpack2(ha[c], h0, h1);
+            const f32x2 ra = pack2(fmaxf(h0, 0.0f), fmaxf(h1, 0.0f));
+            a0 = fma2(ra, w0, a0); a1 = fma2(ra, w1, a1); a2 = fma2(ra, w2, a2);
+            unpack2(hb[c], h0, h1);
+            const f32x2 rb = pack2(fmaxf(h0, 0.0f), fmaxf(h1, 0.0f));
+            b0 = fma2(rb, w0, b0); b1 = fma2(rb, w1, b1); b2 = fma2(rb, w2, b2);
+        }
+    }
+    unpack2(a0, lo, hi); mom_a[0] = add_rn(lo, hi);
+    unpack2(a1, lo, hi); mom_a[1] = add_rn(lo, hi);
+    unpack2(a2, lo, hi); mom_a[2] = add_rn(lo, hi);
+    unpack2(b0, lo, hi); mom_b[0] = add_rn(lo, hi);
+    unpack2(b1, lo, hi); mom_b[1] = add_rn(lo, hi);
+    unpack2(b2, lo, hi); mom_b[2] = add_rn(lo, hi);
+}
+
 // sin and cos together: 3-term Cody-Waite reduction by pi/2 and degree-7/8 minimax polynomials (Cephes
 // coefficients), <= 1.5 ulp on |x| < 1e5 -- the same error class as NumPy's float32 sin/cos (1.45 ulp), see
 // tests/test_kernel_math_models.py.  Huge arguments (a blown-up yaw) take the library's Payne-Hanek path
@@ -507,8 +580,7 @@ __device__ __noinline__ float2 sincos_slow(float x) {
     return make_float2(s, c);
 }
 
-__device__ __forceinline__ void sincos_fast(float x, float &sn, float &cs) {
-    if (fabsf(x) > 1.0e5f) { const float2 r = sincos_slow(x); sn = r.x; cs = r.y; return; }   // also NaN/Inf
+__device__ __forceinline__ void sincos_core(float x, float &sn, float &cs) {  // |x| <= 1e5 (anything else: see callers)
     const float j = rintf(mul_rn(x, 0.636619772367581343f));
     const int q = (int)j;
     float a = fmaf(j, -1.5707962512969970703f, x);
@@ -527,41 +599,71 @@ __device__ __forceinline__ void sincos_fast(float x, float &sn, float &cs) {
     sn = (q & 2) ? -ss : ss;
     cs = ((q + 1) & 2) ? -cc : cc;
 }
+__device__ __forceinline__ void sincos_fast(float x, float &sn, float &cs) {
+    if (fabsf(x) > 1.0e5f) { const float2 r = sincos_slow(x); sn = r.x; cs = r.y; return; }   // also Inf
+    sincos_core(x, sn, cs);
+}
+// The three Euler angles of an env at once: the polynomial path runs unconditionally for all three -- ONE basic block,
+// so the scheduler interleaves the three dependency chains -- and a single, rarely taken branch redoes the angles whose
+// magnitude needs the Payne-Hanek path.  Same values as three sincos_fast calls.
+__device__ __forceinline__ void sincos_fix(float x, float &sn, float &cs) {
+    if (fabsf(x) > 1.0e5f) { const float2 r = sincos_slow(x); sn = r.x; cs = r.y; }
+}
+__device__ __forceinline__ void sincos3_fast(float a, float b, float c, float &sa, float &ca, float &sb, float &cb, float &sc,
+                                             float &cc) {
+    sincos_core(a, sa, ca);
+    sincos_core(b, sb, cb);
+    sincos_core(c, sc, cc);
+    if (fmaxf(fmaxf(fabsf(a), fabsf(b)), fabsf(c)) > 1.0e5f) {  // fmaxf drops NaNs, like the three separate tests
+        sincos_fix(a, sa, ca); sincos_fix(b, sb, cb); sincos_fix(c, sc, cc);
+    }
+}
 
 // new = state + dt * f(state, action[, residual + disturbance])  (`:503-512`; INDI `:304`)
 // Every operation is spelled out (fmaf / __fmul_rn / __fadd_rn / __fsub_rn): nothing is left for the compiler to
 // contract one way in one kernel and another way in the next, so step_kernel and the fused rollout_kernel, which both
 // inline this function, produce the same bits.  The FMA placement is the one the compiler chose when free to (one
 // multiply-add per product term), measured <= 2e-6 scaled error against the reference's unfused float32 evaluation.
+// The three stages of one Euler step.  euler_pre: rotation matrix, body velocity and the residual nets' input vector;
+// [residual nets: residual_mlp for one env, residual_mlp2 for the two envs of a step_kernel_x2 thread]; euler_post:
+// equations of motion and the update.  euler_step = the three in a row; both kernels execute the same operations.
+struct EulerMid {
+    float sph, cph, sth, cth;
+    float r00, r10, r20, r01, r11, r21, r02, r12, r22;
+    float vbx, vby, vbz;
+};
 template <int V>
-__device__ __forceinline__ void euler_step(const StepParams &P, const EnvState<V> &e, const float4 u, EnvState<V> &n) {
-    const float dt = P.dt;
-    float sph, cph, sth, cth, sps, cps;
-    sincos_fast(e.phi, sph, cph);
-    sincos_fast(e.th, sth, cth);
-    sincos_fast(e.psi, sps, cps);
+__device__ __forceinline__ void euler_pre(const EnvState<V> &e, EulerMid &m, float (&x)[10]) {
+    float sps, cps;
+    sincos3_fast(e.phi, e.th, e.psi, m.sph, m.cph, m.sth, m.cth, sps, cps);
+    const float sph = m.sph, cph = m.cph, sth = m.sth, cth = m.cth;
     // R = Rz*Ry*Rx
-    const float r00 = mul_rn(cps, cth), r10 = mul_rn(sps, cth), r20 = -sth;
-    const float r01 = fmaf(mul_rn(sph, sth), cps, -mul_rn(sps, cph));   // sph*sth*cps - sps*cph
-    const float r11 = fmaf(mul_rn(sph, sps), sth, mul_rn(cph, cps));    // sph*sps*sth + cph*cps
-    const float r21 = mul_rn(sph, cth);
-    const float r02 = fmaf(mul_rn(sth, cph), cps, mul_rn(sph, sps));    // sph*sps + sth*cph*cps
-    const float r12 = fmaf(mul_rn(sps, sth), cph, -mul_rn(sph, cps));   // -sph*cps + sps*sth*cph
-    const float r22 = mul_rn(cph, cth);
-    const float vbx = fmaf(e.vz, r20, fmaf(e.vy, r10, mul_rn(e.vx, r00)));
-    const float vby = fmaf(e.vz, r21, fmaf(e.vy, r11, mul_rn(e.vx, r01)));
-    const float vbz = fmaf(e.vz, r22, fmaf(e.vy, r12, mul_rn(e.vx, r02)));
+    m.r00 = mul_rn(cps, cth); m.r10 = mul_rn(sps, cth); m.r20 = -sth;
+    m.r01 = fmaf(mul_rn(sph, sth), cps, -mul_rn(sps, cph));   // sph*sth*cps - sps*cph
+    m.r11 = fmaf(mul_rn(sph, sps), sth, mul_rn(cph, cps));    // sph*sps*sth + cph*cps
+    m.r21 = mul_rn(sph, cth);
+    m.r02 = fmaf(mul_rn(sth, cph), cps, mul_rn(sph, sps));    // sph*sps + sth*cph*cps
+    m.r12 = fmaf(mul_rn(sps, sth), cph, -mul_rn(sph, cps));   // -sph*cps + sps*sth*cph
+    m.r22 = mul_rn(cph, cth);
+    m.vbx = fmaf(e.vz, m.r20, fmaf(e.vy, m.r10, mul_rn(e.vx, m.r00)));
+    m.vby = fmaf(e.vz, m.r21, fmaf(e.vy, m.r11, mul_rn(e.vx, m.r01)));
+    m.vbz = fmaf(e.vz, m.r22, fmaf(e.vy, m.r12, mul_rn(e.vx, m.r02)));
+    if (V == kE2E) {
+        x[0] = e.w[0]; x[1] = e.w[1]; x[2] = e.w[2]; x[3] = e.w[V == kE2E ? 3 : 0];
+        x[4] = m.vbx; x[5] = m.vby; x[6] = m.vbz; x[7] = e.p; x[8] = e.q; x[9] = e.r;
+    }
+}
 
+template <int V>
+__device__ __forceinline__ void euler_post(const StepParams &P, const EnvState<V> &e, const float4 u, const EulerMid &m,
+                                           const float thr, const float (&mom)[3], EnvState<V> &n) {
+    const float dt = P.dt;
+    const float sph = m.sph, cph = m.cph, sth = m.sth, cth = m.cth;
+    const float r00 = m.r00, r10 = m.r10, r20 = m.r20, r01 = m.r01, r11 = m.r11, r21 = m.r21, r02 = m.r02, r12 = m.r12, r22 = m.r22;
+    const float vbx = m.vbx, vby = m.vby, vbz = m.vbz;
     float Dx, Dy, T, dp, dq, dr;
     if (V == kE2E) {
         const float w1 = e.w[0], w2 = e.w[1], w3 = e.w[2], w4 = e.w[V == kE2E ? 3 : 0];
-        const float x[10] = {w1, w2, w3, w4, vbx, vby, vbz, e.p, e.q, e.r};
-        float thr, mom[3];
-#ifdef QS_EXP_NOMLP  // experiment only (tools/exp_variants.sh): what the step costs without the residual MLPs
-        thr = mul_rn(x[4], P.b2[0]); mom[0] = mul_rn(x[5], P.b2[1]); mom[1] = mul_rn(x[6], P.b2[2]); mom[2] = mul_rn(x[7], P.b2[3]);
-#else
-        residual_mlp(P, x, thr, mom);
-#endif
         const float Mx = add_rn(mom[0], e.dist[0]), My = add_rn(mom[1], e.dist[1]), Mz = add_rn(mom[2], e.dist[2]);
         const float Fz = add_rn(thr, e.dist[5]);
         const float W1 = fmaf(4000.f, w1, 7000.f), W2 = fmaf(4000.f, w2, 7000.f);
@@ -621,6 +723,22 @@ __device__ __forceinline__ void euler_step(const StepParams &P, const EnvState<V
     n.vx = fmaf(dt, dvx, e.vx); n.vy = fmaf(dt, dvy, e.vy); n.vz = fmaf(dt, dvz, e.vz);
     n.phi = fmaf(dt, dphi, e.phi); n.th = fmaf(dt, dth, e.th); n.psi = fmaf(dt, dpsi, e.psi);
     n.p = fmaf(dt, dp, e.p); n.q = fmaf(dt, dq, e.q); n.r = fmaf(dt, dr, e.r);
+}
+
+template <int V>
+__device__ __forceinline__ void euler_step(const StepParams &P, const EnvState<V> &e, const float4 u, EnvState<V> &n) {
+    EulerMid m;
+    float x[10];
+    euler_pre<V>(e, m, x);
+    float thr = 0.0f, mom[3] = {0.0f, 0.0f, 0.0f};
+    if (V == kE2E) {
+#ifdef QS_EXP_NOMLP  // experiment only: what the step costs without the residual MLPs
+        thr = mul_rn(x[4], P.b2[0]); mom[0] = mul_rn(x[5], P.b2[1]); mom[1] = mul_rn(x[6], P.b2[2]); mom[2] = mul_rn(x[7], P.b2[3]);
+#else
+        residual_mlp(P, x, thr, mom);
+#endif
+    }
+    euler_post<V>(P, e, u, m, thr, mom, n);
 }
 
 // ------------------------------------------------------------------------------------------------ async-proxy primitives
@@ -789,6 +907,107 @@ __device__ __forceinline__ void issue_warp_tile(const StepParams &P, unsigned ch
     }
 }
 
+// Start of a step launch, after the CTA's own prologue (barrier init, track table): wait for what this CTA depends on
+// and return the launch's RNG epoch.  Classic launch: trigger the next grid's early start, wait for the whole previous
+// grid (griddepcontrol.wait), read the epoch (advanced by the last CTA of this launch to FINISH, step_launch_end).
+// Chained launch (P.chain): the epoch is read and advanced -- by the last CTA to ARRIVE -- BEFORE this CTA lets the
+// next launch start, so every CTA of the next launch reads epoch + 1 although this launch is still running; then only
+// CTA b of the previous launch is awaited (it stepped the very tiles this CTA is about to load).  chain_seq (thread 0):
+// how many chained launches this CTA slot had started before this one.
+__device__ __forceinline__ unsigned long long step_launch_begin(const StepParams &P, unsigned &chain_seq) {
+    const int tid = threadIdx.x;
+    chain_seq = 0;
+    if (P.chain == nullptr) {
+        pdl_launch_dependents();
+        pdl_wait();
+        return load_epoch(P.epoch);
+    }
+    __shared__ unsigned long long s_epoch;
+    if (!P.chain_wait) pdl_wait();  // the previous kernel is not a chained step of this env: wait for all of it
+    if (tid == 0) {
+        const unsigned long long ep = load_epoch(P.epoch);
+        s_epoch = ep;
+        if (atomicAdd(P.epoch + 1, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+            *reinterpret_cast<volatile unsigned long long *>(P.epoch + 1) = 0ull;
+            *reinterpret_cast<volatile unsigned long long *>(P.epoch) = ep + 1ull;
+        }
+        chain_seq = atomicAdd(P.chain + 2 * blockIdx.x, 1u);
+        __threadfence();
+    }
+    __syncthreads();
+    const unsigned long long launch_epoch = s_epoch;
+    pdl_launch_dependents();
+    if (P.chain_wait) {  // CTA b of the previous launch wrote the state blocks this CTA is about to load
+        if (tid == 0)
+            while (ld_acquire_gpu(P.chain + 2 * blockIdx.x + 1) != chain_seq) __nanosleep(40);
+        __syncthreads();
+        if ((tid & 31) == 0) fence_proxy_async_all();  // its generic-proxy stores, before this warp's bulk (async-proxy) loads
+    }
+    return launch_epoch;
+}
+
+// Per-thread tallies of a launch -> the CTA's own statistics slot (warp-shuffle reduction, then ONE plain read-modify-
+// write per CTA: no atomics -- 740-1184 CTAs hammering one address cost 1-4 us per launch; qs_get_stats sums the slots).
+struct StepTally {
+    float reward = 0.0f;
+    unsigned act = 0, done = 0, tr = 0, gp = 0, gc = 0, gr = 0, ob = 0;
+    __device__ __forceinline__ void add(float r, uint32_t fl) {
+        reward += r;
+        act += 1; done += (fl & F_DONE) != 0; tr += (fl & F_TRUNC) != 0; gp += (fl & F_PASSED) != 0;
+        gc += (fl & F_COLLISION) != 0; gr += (fl & F_GROUND) != 0; ob += (fl & F_OOB) != 0;
+    }
+};
+template <int kWarps>
+__device__ __forceinline__ void step_stats_flush(const StepParams &P, StepTally t) {
+    __shared__ float s_red_f[kWarps];
+    __shared__ unsigned s_red_u[kWarps][7];
+    const int tid = threadIdx.x;
+    const unsigned full_mask = 0xffffffffu;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t.reward += __shfl_xor_sync(full_mask, t.reward, o);
+    t.act = __reduce_add_sync(full_mask, t.act); t.done = __reduce_add_sync(full_mask, t.done);
+    t.tr = __reduce_add_sync(full_mask, t.tr); t.gp = __reduce_add_sync(full_mask, t.gp);
+    t.gc = __reduce_add_sync(full_mask, t.gc); t.gr = __reduce_add_sync(full_mask, t.gr);
+    t.ob = __reduce_add_sync(full_mask, t.ob);
+    if ((tid & 31) == 0) {
+        const int w = tid >> 5;
+        s_red_f[w] = t.reward;
+        s_red_u[w][0] = t.act; s_red_u[w][1] = t.done; s_red_u[w][2] = t.tr; s_red_u[w][3] = t.gp;
+        s_red_u[w][4] = t.gc; s_red_u[w][5] = t.gr; s_red_u[w][6] = t.ob;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float r = 0.0f;
+        unsigned c[7] = {0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            r += s_red_f[w];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) c[k] += s_red_u[w][k];
+        }
+        if (c[0]) {
+            Stats *st = P.stats + blockIdx.x;
+            st->reward_sum += (double)r;
+            st->env_steps += c[0]; st->dones += c[1]; st->truncated += c[2]; st->gates_passed += c[3];
+            st->gate_collisions += c[4]; st->ground_collisions += c[5]; st->out_of_bounds += c[6];
+        }
+    }
+}
+
+// End of a step launch: called by every thread after the CTA's last store / draw (lane 0 of each warp has already
+// waited for its bulk stores: .read for a classic launch, full completion for a chained one).
+template <int kWarps>
+__device__ __forceinline__ void step_launch_end(const StepParams &P, const StepTally &tally, unsigned chain_seq) {
+    const int tid = threadIdx.x;
+    __syncthreads();  // every warp of the CTA is past its last reset draw (and, chained, its last store)
+    if (tid == 0 && P.advance_epoch && !P.chain) epoch_arrive(P);
+    if (P.stats) step_stats_flush<kWarps>(P, tally);
+    if (tid == 0 && P.chain) {  // chained: hand this CTA's tiles (and its stats slot) to CTA b of the next launch
+        __threadfence();
+        st_release_gpu(P.chain + 2 * blockIdx.x + 1, chain_seq + 1u);
+    }
+}
+
 // Persistent CTAs (grid = SMs x resident CTAs) of four INDEPENDENT warps.  Each warp owns 32 envs of the CTA's
 // 128-env tile and runs its own kStages-deep ring of shared-memory stages: lane 0 refills a stage with TMA bulk
 // loads the moment the warp has copied it to registers, and waits on the stage's mbarrier for the bytes to land.
@@ -829,37 +1048,8 @@ __global__ void __launch_bounds__(StepCta<V>::THREADS, StepCta<V>::MIN_CTAS) ste
     __syncthreads();  // barrier init and track table visible to everyone
     // Everything above touched only launch constants.  From here on we read and write simulator state that the
     // previous step's grid may still be producing (programmatic dependent launch).
-    unsigned long long launch_epoch;  // the RNG epoch of this launch (the same for every CTA)
-    unsigned chain_seq = 0;           // thread 0: how many chained launches this CTA slot had started before this one
-    if (P.chain == nullptr) {
-        pdl_launch_dependents();
-        pdl_wait();
-        launch_epoch = load_epoch(P.epoch);  // advanced by the last CTA of this launch to FINISH (epoch_arrive)
-    } else {
-        // Chained launch.  Order matters: the epoch is read and advanced (by the last CTA to arrive) BEFORE this CTA
-        // lets the next launch start, so every CTA of the next launch reads epoch + 1 although this launch still runs.
-        __shared__ unsigned long long s_epoch;
-        if (!P.chain_wait) pdl_wait();  // the previous kernel is not a chained step of this env: wait for all of it
-        if (tid == 0) {
-            const unsigned long long ep = load_epoch(P.epoch);
-            s_epoch = ep;
-            if (atomicAdd(P.epoch + 1, 1ull) == (unsigned long long)gridDim.x - 1ull) {
-                *reinterpret_cast<volatile unsigned long long *>(P.epoch + 1) = 0ull;
-                *reinterpret_cast<volatile unsigned long long *>(P.epoch) = ep + 1ull;
-            }
-            chain_seq = atomicAdd(P.chain + 2 * blockIdx.x, 1u);
-            __threadfence();
-        }
-        __syncthreads();
-        launch_epoch = s_epoch;
-        pdl_launch_dependents();
-        if (P.chain_wait) {  // CTA b of the previous launch wrote the state blocks this CTA is about to load
-            if (tid == 0)
-                while (ld_acquire_gpu(P.chain + 2 * blockIdx.x + 1) != chain_seq) __nanosleep(40);
-            __syncthreads();
-            if (lane == 0) fence_proxy_async_all();  // its generic-proxy stores, before this warp's bulk (async-proxy) loads
-        }
-    }
+    unsigned chain_seq;
+    const unsigned long long launch_epoch = step_launch_begin(P, chain_seq);  // the RNG epoch of this launch
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) {
@@ -869,8 +1059,7 @@ __global__ void __launch_bounds__(StepCta<V>::THREADS, StepCta<V>::MIN_CTAS) ste
     }
 
     // ------------------------------------------------------------------------------------------ consumers
-    float reward_acc = 0.0f;  // stats are reduced once per CTA lifetime, not per tile
-    unsigned c_act = 0, c_done = 0, c_tr = 0, c_gp = 0, c_gc = 0, c_gr = 0, c_ob = 0;
+    StepTally tally;  // stats are reduced once per CTA lifetime, not per tile
     const bool write_obs_tile = P.mode != kModePause;
     const bool fused_reset = P.mode == kModeNormal && P.reset_source == kResetDevice;
     float *const warp_obs = s_obs + warp * slice;
@@ -1019,11 +1208,7 @@ __global__ void __launch_bounds__(StepCta<V>::THREADS, StepCta<V>::MIN_CTAS) ste
                         bulk_store(reinterpret_cast<unsigned char *>(P.peer_obs[p]) + ((P.peer_row_offset >> 5) + b32) * (long long)pkb, warp_obs, pkb);
                 }
                 obs_in_flight = true;
-                if (P.stats && active) {
-                    reward_acc += reward;
-                    c_act += 1; c_done += (fl & F_DONE) != 0; c_tr += (fl & F_TRUNC) != 0; c_gp += (fl & F_PASSED) != 0;
-                    c_gc += (fl & F_COLLISION) != 0; c_gr += (fl & F_GROUND) != 0; c_ob += (fl & F_OOB) != 0;
-                }
+                if (P.stats && active) tally.add(reward, fl);
                 continue;
             }
             const long long rem = P.n - base;
@@ -1057,58 +1242,205 @@ __global__ void __launch_bounds__(StepCta<V>::THREADS, StepCta<V>::MIN_CTAS) ste
                 __syncwarp();
             }
         }
-        if (P.stats && active) {
-            reward_acc += reward;
-            c_act += 1; c_done += (fl & F_DONE) != 0; c_tr += (fl & F_TRUNC) != 0; c_gp += (fl & F_PASSED) != 0;
-            c_gc += (fl & F_COLLISION) != 0; c_gr += (fl & F_GROUND) != 0; c_ob += (fl & F_OOB) != 0;
-        }
+        if (P.stats && active) tally.add(reward, fl);
     }
     if (lane == 0 && write_obs_tile) {
         if (P.chain) bulk_store_wait_all();  // chained: the rows have LANDED before the next launch's CTA may rewrite them
         else bulk_store_wait_read();         // shared memory must outlive the last bulk read
     }
-    __syncthreads();  // every warp of the CTA is past its last reset draw (and, chained, its last store)
-    if (tid == 0 && P.advance_epoch && !P.chain) epoch_arrive(P);
+    step_launch_end<kWarps>(P, tally, chain_seq);
+}
 
-    if (P.stats) {  // warp-shuffle reduction, then ONE plain read-modify-write per CTA on the CTA's own slot:
-                    // no atomics (740-1184 CTAs hammering one address cost 1-4 us per launch), summed by qs_get_stats
-        __shared__ float s_red_f[kWarps];
-        __shared__ unsigned s_red_u[kWarps][7];
-        const unsigned full_mask = 0xffffffffu;
+// ------------------------------------------------------------------------------------------------ E2E, two envs per thread
+// EXPERIMENT, opt-in (QS_STEP_X2=1), measured SLOWER than step_kernel<e2e> on B200 (75 vs 57 us per step at N = 2^20).
+// The E2E step is bound by instruction issue, not by HBM (with chained launches its memory pipeline alone runs at 0.96 of
+// the roofline, the full kernel at 0.80): 615 of its 1430 warp-instructions per 32 envs are the residual nets, and a third
+// of those only fetch weights (LDCU / LDC).  Here a thread steps TWO envs (a lane of warp-tile a and the same lane of
+// warp-tile b): every weight fetch feeds both (residual_mlp2: 173 LDCU.128 for 672 FFMA2) and the per-tile bookkeeping
+// is paid once per 64 envs -- 15 % fewer instructions per env.  But the loop body doubles (the nets must stay fully
+// unrolled, see residual_mlp), only 12-16 warps fit per SM (138 registers), and the per-warp issue rate does not rise
+// with the second independent chain: the instruction fetch, not the dependency latency, is what limits a warp here.
+// Kept because it is bit-identical per env to step_kernel (tests/test_gpu_chain.py) and documents the dead end.
+// Shared memory per warp: a ring of FOUR stage buffers, used in pairs.  Iteration i waits for pair i&1, copies it to
+// registers, and -- the buffers now being free -- stages its two observation tiles in them for the TMA bulk stores;
+// half an iteration later (behind the dynamics of iteration i+1) those stores have long read the buffers and lane 0
+// refills them with the tiles of iteration i+2.  No separate observation staging: 13.5 KB per warp.
+// Scope: float32 observations that fit a stage buffer (obs_len <= 27: gates_ahead <= 1), no peer stores, no L2 hints;
+// everything else runs step_kernel<kE2E>.
+constexpr int kX2Warps = 4, kX2Bufs = 4;
+__host__ __device__ constexpr size_t step_x2_smem_bytes(int n_gates) {
+    return kBarBytes + (size_t)kX2Warps * kX2Bufs * Stage<kE2E>::BYTES + (size_t)n_gates * kTrackRow * 4;
+}
+__host__ __device__ constexpr bool step_x2_supports(int obs_len) { return 32 * obs_len * 4 <= (int)Stage<kE2E>::BYTES; }
+
+#ifndef QS_X2_MIN_CTAS
+#define QS_X2_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(kX2Warps * 32, QS_X2_MIN_CTAS) step_kernel_x2(const __grid_constant__ StepParams P) {
+    constexpr int V = kE2E;
+    using S = Stage<V>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw) + warp * kX2Bufs;                  // this warp's barriers
+    unsigned char *bufs = smem_raw + kBarBytes + warp * (kX2Bufs * S::BYTES);                  // this warp's ring
+    float *s_track = reinterpret_cast<float *>(smem_raw + kBarBytes + kX2Warps * kX2Bufs * S::BYTES);
+    const long long n_tiles = P.tile_end * (kBlock / 32);                                      // in 32-env warp-tiles
+    const long long tile0 = P.tile_begin * (kBlock / 32) + (long long)blockIdx.x * kX2Warps + warp;
+    const long long stride = (long long)gridDim.x * kX2Warps;
+
+    if (lane == 0) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) reward_acc += __shfl_xor_sync(full_mask, reward_acc, o);
-        c_act = __reduce_add_sync(full_mask, c_act); c_done = __reduce_add_sync(full_mask, c_done);
-        c_tr = __reduce_add_sync(full_mask, c_tr); c_gp = __reduce_add_sync(full_mask, c_gp);
-        c_gc = __reduce_add_sync(full_mask, c_gc); c_gr = __reduce_add_sync(full_mask, c_gr);
-        c_ob = __reduce_add_sync(full_mask, c_ob);
-        if ((tid & 31) == 0) {
-            const int w = tid >> 5;
-            s_red_f[w] = reward_acc;
-            s_red_u[w][0] = c_act; s_red_u[w][1] = c_done; s_red_u[w][2] = c_tr; s_red_u[w][3] = c_gp;
-            s_red_u[w][4] = c_gc; s_red_u[w][5] = c_gr; s_red_u[w][6] = c_ob;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            float r = 0.0f;
-            unsigned c[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int b = 0; b < kX2Bufs; ++b) mbar_init(&full[b], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < P.n_gates * kTrackRow; i += kX2Warps * 32) s_track[i] = P.track[i];
+    __syncthreads();
+    unsigned chain_seq;
+    const unsigned long long launch_epoch = step_launch_begin(P, chain_seq);
+    if (lane == 0) {
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) {
-                r += s_red_f[w];
-#pragma unroll
-                for (int k = 0; k < 7; ++k) c[k] += s_red_u[w][k];
-            }
-            if (c[0]) {
-                Stats *st = P.stats + blockIdx.x;
-                st->reward_sum += (double)r;
-                st->env_steps += c[0]; st->dones += c[1]; st->truncated += c[2]; st->gates_passed += c[3];
-                st->gate_collisions += c[4]; st->ground_collisions += c[5]; st->out_of_bounds += c[6];
-            }
+        for (int b = 0; b < kX2Bufs; ++b) {
+            const long long t = tile0 + (long long)b * stride;
+            if (t < n_tiles) issue_warp_tile<V, false>(P, bufs + b * S::BYTES, &full[b], t * 32, 0ull, 0ull);
         }
     }
-    if (tid == 0 && P.chain) {  // chained: hand this CTA's tiles (and its stats slot) to CTA b of the next launch
-        __threadfence();
-        st_release_gpu(P.chain + 2 * blockIdx.x + 1, chain_seq + 1u);
+
+    StepTally tally;
+    const bool write_obs_tile = P.mode != kModePause;
+    const bool fused_reset = P.mode == kModeNormal && P.reset_source == kResetDevice;
+    const uint32_t row_bytes = (uint32_t)P.obs_len * 4u;
+    int it = 0;
+    for (long long tile_a = tile0; tile_a < n_tiles; tile_a += 2 * stride, ++it) {
+        const int pair = it & 1;
+        const uint32_t phase = (uint32_t)(it >> 1) & 1u;
+        unsigned char *const buf[2] = {bufs + (2 * pair) * S::BYTES, bufs + (2 * pair + 1) * S::BYTES};
+        const long long tile[2] = {tile_a, tile_a + stride};
+        const bool have_b = tile[1] < n_tiles;  // warp-uniform: the last iteration of a warp may hold one tile only
+        mbar_wait(&full[2 * pair], phase);
+        if (have_b) mbar_wait(&full[2 * pair + 1], phase);
+
+        // ---- stage buffers -> registers
+        EnvState<V> e[2], n[2];
+        float4 u[2];
+        uint32_t tg[2], sc[2];
+        bool active[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const unsigned char *st = buf[h];
+            const float4 a = reinterpret_cast<const float4 *>(st + S::P0)[lane];
+            const float4 b = reinterpret_cast<const float4 *>(st + S::P1)[lane];
+            const float4 c = reinterpret_cast<const float4 *>(st + S::P2)[lane];
+            const float4 d = reinterpret_cast<const float4 *>(st + S::P3)[lane];
+            const float4 da = reinterpret_cast<const float4 *>(st + S::DA)[lane];
+            const float2 db = reinterpret_cast<const float2 *>(st + S::DB)[lane];
+            e[h].x = a.x; e[h].y = a.y; e[h].z = a.z; e[h].vx = a.w; e[h].vy = b.x; e[h].vz = b.y; e[h].phi = b.z; e[h].th = b.w;
+            e[h].psi = c.x; e[h].p = c.y; e[h].q = c.z; e[h].r = c.w;
+            e[h].w[0] = d.x; e[h].w[1] = d.y; e[h].w[2] = d.z; e[h].w[3] = d.w;
+            e[h].dist[0] = da.x; e[h].dist[1] = da.y; e[h].dist[2] = da.z; e[h].dist[5] = da.w; e[h].dist[3] = db.x; e[h].dist[4] = db.y;
+            u[h] = reinterpret_cast<const float4 *>(st + S::ACT)[lane];
+            const uint32_t meta = reinterpret_cast<const uint32_t *>(st + S::META)[lane];
+            tg[h] = meta >> 24; sc[h] = meta & kStepMask;
+            active[h] = (h == 0 || have_b) && (tile[h] * 32 + lane < P.n);
+        }
+        if (!have_b) { tg[1] = 0; sc[1] = 0; }  // whatever bytes an unused buffer holds: keep the table index in range
+        __syncwarp();  // the warp's inputs are in registers: both buffers are free
+
+        // ---- the OTHER pair of buffers staged the previous iteration's observation tiles: as soon as those bulk stores
+        // have read them (they were issued at the end of that iteration) refill them with the tiles of the next one --
+        // a whole iteration of lead for the loads
+        if (it > 0 && lane == 0) {
+            bulk_store_wait_read();
+            const long long na = tile_a + 2 * stride;
+            unsigned char *nb = bufs + (2 * (pair ^ 1)) * S::BYTES;
+            if (na < n_tiles) issue_warp_tile<V, false>(P, nb, &full[2 * (pair ^ 1)], na * 32, 0ull, 0ull);
+            if (na + stride < n_tiles) issue_warp_tile<V, false>(P, nb + S::BYTES, &full[2 * (pair ^ 1) + 1], (na + stride) * 32, 0ull, 0ull);
+        }
+
+        // ---- dynamics: the two envs share every weight fetch
+        EulerMid mid[2];
+        float xin[2][10], thr[2], mom[2][3];
+        euler_pre<V>(e[0], mid[0], xin[0]);
+        euler_pre<V>(e[1], mid[1], xin[1]);
+        residual_mlp2(P, xin[0], xin[1], thr[0], mom[0], thr[1], mom[1]);
+        euler_post<V>(P, e[0], u[0], mid[0], thr[0], mom[0], n[0]);
+        euler_post<V>(P, e[1], u[1], mid[1], thr[1], mom[1], n[1]);
+
+        // The rest runs in phases over both envs (not env by env), so that each phase is one large basic block in which
+        // the two independent instruction streams interleave.
+        float reward[2]; bool dn[2]; uint32_t fl[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) reward_and_flags<V>(P, s_track, e[h], n[h], tg[h], sc[h], reward[h], dn[h], fl[h]);
+        // ---- branch logic (`:568-585`)
+        bool write_world[2] = {active[0], active[1]}, write_dist[2] = {false, false};
+        if (fused_reset) {  // warp-uniform branch: the whole warp takes part in the draws
+            const bool need0 = dn[0] && active[0], need1 = dn[1] && active[1];
+            if (__any_sync(0xffffffffu, need0 | need1)) {  // scratch = a tile's own (free) stage buffer
+                draw_reset_warp<V>(P, tile[0] * 32, need0, reinterpret_cast<uint4 *>(buf[0]), n[0], launch_epoch);
+                draw_reset_warp<V>(P, tile[1] * 32, need1, reinterpret_cast<uint4 *>(buf[1]), n[1], launch_epoch);
+            }
+            if (need0) { tg[0] = 0; sc[0] = 0; write_dist[0] = true; }
+            if (need1) { tg[1] = 0; sc[1] = 0; write_dist[1] = true; }
+        } else if (P.mode == kModePauseIfCollision) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (dn[h]) { n[h] = e[h]; write_world[h] = false; }
+        } else if (P.mode == kModePause) {
+            write_world[0] = write_world[1] = false;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const long long env = tile[h] * 32 + lane;
+            unsigned char *const gblk = P.s.base + tile[h] * (long long)Blk<V>::BYTES;  // this warp-tile's block
+            const uint8_t dn8 = (P.mode == kModePause) ? (uint8_t)0 : (uint8_t)(dn[h] ? 1 : 0);
+            if (active[h]) {
+                reinterpret_cast<uint32_t *>(gblk + S::META)[lane] = (tg[h] << 24) | sc[h];
+                P.rew[env] = reward[h];
+                P.done[env] = dn8;
+                if (P.flags) P.flags[env] = (uint8_t)fl[h];
+            }
+            if (write_world[h]) {
+                reinterpret_cast<float4 *>(gblk + S::P0)[lane] = make_float4(n[h].x, n[h].y, n[h].z, n[h].vx);
+                reinterpret_cast<float4 *>(gblk + S::P1)[lane] = make_float4(n[h].vy, n[h].vz, n[h].phi, n[h].th);
+                reinterpret_cast<float4 *>(gblk + S::P2)[lane] = make_float4(n[h].psi, n[h].p, n[h].q, n[h].r);
+                reinterpret_cast<float4 *>(gblk + S::P3)[lane] = make_float4(n[h].w[0], n[h].w[1], n[h].w[2], n[h].w[3]);
+            }
+            if (write_dist[h]) {
+                reinterpret_cast<float4 *>(gblk + S::DA)[lane] = make_float4(n[h].dist[0], n[h].dist[1], n[h].dist[2], n[h].dist[5]);
+                reinterpret_cast<float2 *>(gblk + S::DB)[lane] = make_float2(n[h].dist[3], n[h].dist[4]);
+            }
+            if (P.stats && active[h]) tally.add(reward[h], fl[h]);
+        }
+        if (write_obs_tile) {
+            __syncwarp();  // (a reset draw may just have used the buffers as scratch)
+            write_obs<V>(P, s_track, n[0], tg[0], reinterpret_cast<float *>(buf[0]) + lane * P.obs_len);
+            if (have_b) write_obs<V>(P, s_track, n[1], tg[1], reinterpret_cast<float *>(buf[1]) + lane * P.obs_len);
+            fence_proxy_async();
+            __syncwarp();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (h == 1 && !have_b) break;
+                const long long base = tile[h] * 32;
+                const float *tile_obs = reinterpret_cast<const float *>(buf[h]);
+                const long long rem = P.n - base;
+                const int rows = rem < 32 ? (rem < 0 ? 0 : (int)rem) : 32;
+                float *dst = P.obs + base * P.obs_len;
+                const uint32_t bytes = (uint32_t)rows * row_bytes;
+                const bool bulk = ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) && ((bytes & 15u) == 0);
+                if (bulk) {  // the warp's rows are contiguous in the (N,D) output: one TMA bulk store
+                    if (lane == 0 && bytes) bulk_store(dst, tile_obs, bytes);
+                } else {
+#pragma unroll 1
+                    for (int i = lane; i < rows * P.obs_len; i += 32) dst[i] = tile_obs[i];
+                }
+            }
+            __syncwarp();
+        }
     }
+    if (lane == 0 && write_obs_tile) {
+        if (P.chain) bulk_store_wait_all();
+        else bulk_store_wait_read();
+    }
+    step_launch_end<kX2Warps>(P, tally, chain_seq);
 }
 
 // ------------------------------------------------------------------------------------------------ observe / reset kernels

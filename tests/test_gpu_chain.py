@@ -91,3 +91,39 @@ def test_chained_graph_replays_equal_classic_launches(variant, n, eager_between,
         for x, y in zip(final, ref_final):
             np.testing.assert_array_equal(x, y)
         assert st == ref_st
+
+
+@pytest.mark.parametrize("ga,pic", [(1, False), (0, False), (1, True)])
+def test_two_envs_per_thread_kernel_equals_one_env_kernel(ga, pic, tracks, monkeypatch):
+    """step_kernel_x2 (E2E, a thread steps two envs and shares the residual nets' weight fetches between them) against
+    step_kernel<e2e>: every output of every step, the state and the statistics, bit for bit; ragged N, fused resets."""
+    import torch
+    import optimal_quad_control_rl_b200 as Q
+    n, steps = 300_007, 12
+    res = []
+    for x2 in ("1", "0"):
+        monkeypatch.setenv("QS_STEP_X2", x2)
+        env = make_env("e2e", n, tracks, ga=ga, pic=pic, reset_rng="device", seed=9)
+        env.disturbance_ranges = Q.training_disturbance_ranges()
+        env.max_steps = 5
+        env.enable_stats()
+        env.reset_tensor()
+        gen = torch.Generator(device="cuda").manual_seed(4)
+        outs = []
+        for _ in range(steps):
+            a = torch.rand((n, 4), device="cuda", generator=gen) * 2 - 1
+            outs.append([t.clone() for t in env.step_tensor(a)])
+        torch.cuda.synchronize()
+        res.append((outs, env.world_states.copy(), env.target_gates.copy(), env.step_counts.copy(), env.disturbances.copy(),
+                    env.stats()))
+        env.close()
+    (oa, wa, ta, sa, da, sta), (ob, wb, tb, sb, db, stb) = res
+    for t, (x, y) in enumerate(zip(oa, ob)):
+        for k, (p, q) in enumerate(zip(x, y)):
+            assert torch.equal(p, q), ("step", t, "tensor", k)
+    np.testing.assert_array_equal(wa, wb)
+    np.testing.assert_array_equal(ta, tb)
+    np.testing.assert_array_equal(sa, sb)
+    np.testing.assert_array_equal(da, db)
+    assert sta["dones"] > 0 and {k: v for k, v in sta.items() if k != "reward_sum"} == {k: v for k, v in stb.items() if k != "reward_sum"}
+    assert abs(sta["reward_sum"] - stb["reward_sum"]) <= 1e-6 * max(1.0, abs(stb["reward_sum"]))  # other partition of the float sums
