@@ -641,6 +641,7 @@ def run_ours(a):
     elif roll:
         launches = K // T if fused else 2 * K
     st = env.stats(reset=True)
+    chained = env.chained_launch_count  # captured steps that wait for their predecessor CTA by CTA (per graph, not per replay)
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -730,9 +731,9 @@ def run_ours(a):
         except Exception:
             pass
         kernel_ms = ms / K  # the timed region is exactly K launches of the step kernel, back to back
-        # the library pins the INDI state in L2 by default (csrc/quadsim_capi.cu; QS_L2_HINTS overrides): say so, the
+        # the library asks the L2 to keep the state by default (csrc/quadsim_capi.cu; QS_L2_HINTS overrides): say so, the
         # roofline fraction is still computed from the fixed algorithmic bytes and can then exceed 1
-        hints = os.environ.get("QS_L2_HINTS", "1" if a.variant == "indi" else "0") not in ("0", "")
+        hints = os.environ.get("QS_L2_HINTS", "1") not in ("0", "")
         state_mb = n * (56 if a.variant == "indi" else 92) / 1e6
         l2_note = (f"; state ({state_mb:.0f} MB) loaded/stored with L2 evict_last, streams evict_first: it stays resident "
                    f"between step launches up to {os.environ.get('QS_L2_KEEP_MB', '56')} MB") if hints else ""
@@ -749,7 +750,7 @@ def run_ours(a):
                        "done_rate": st["dones"] / max(1, st["env_steps"]) if not a.no_stats else None,
                        "launch": timer.launch_mode, "cpu_affinity_cores": pinned_cpus,
                        # steps inside a graph that depend on their predecessor CTA by CTA instead of grid by grid
-                       "chained_launches": env.chained_launch_count},
+                       "chained_launches_per_graph": chained},
             "replay_ms_per_step": replays,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,

@@ -68,6 +68,7 @@ struct qs_env {
     unsigned int *chain_dev = nullptr;
     uint64_t chain_tag = 0;
     unsigned long long chain_capture = 0;
+    cudaGraphNode_t chain_node = nullptr;  // the graph node of that launch: the next step chains only if it depends on exactly this node
     bool chain_x2 = false;          // kernel of the last chainable launch (a chain never spans two kernels)
     // E2E with two envs per thread (step_kernel_x2; QS_STEP_X2=0 turns it off): used when every warp of its grid gets
     // at least two warp-tiles and the launch needs none of the features only step_kernel has (see launch_step)
@@ -570,9 +571,14 @@ static int launch_step(qs_env *e, long long t0, long long t1, int advance_epoch,
     if (chainable) {
         cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
         unsigned long long cid = 0;
-        if (cudaStreamGetCaptureInfo(stream, &cst, &cid) != cudaSuccess) { cudaGetLastError(); cst = cudaStreamCaptureStatusNone; }
+        const cudaGraphNode_t *deps = nullptr;
+        size_t n_deps = 0;
+        if (cudaStreamGetCaptureInfo(stream, &cst, &cid, nullptr, &deps, &n_deps) != cudaSuccess) { cudaGetLastError(); cst = cudaStreamCaptureStatusNone; }
         const bool capturing = cst == cudaStreamCaptureStatusActive;
-        if (capturing && cid == e->chain_capture && e->chain_tag != 0 && g_pdl_serial.load() == e->chain_tag && e->chain_x2 == x2)
+        // ... and only if that launch is the ONLY thing this one depends on: a foreign kernel captured in between (it may
+        // produce the actions) is then waited for as a whole, like everything else
+        if (capturing && cid == e->chain_capture && e->chain_tag != 0 && g_pdl_serial.load() == e->chain_tag && e->chain_x2 == x2 &&
+            n_deps == 1 && deps && deps[0] == e->chain_node && e->chain_node != nullptr)
             P.chain_wait = 1;
         e->chain_capture = capturing ? cid : 0ull;
         e->chain_x2 = x2;
@@ -600,6 +606,14 @@ static int launch_step(qs_env *e, long long t0, long long t1, int advance_epoch,
     QS_CUDA(e, cudaLaunchKernelExC(&cfg, x2 ? (const void *)qs::step_kernel_x2 : step_function(e), args));
     const uint64_t tag = ++g_pdl_serial;
     e->chain_tag = chainable ? tag : 0;
+    e->chain_node = nullptr;
+    if (chainable && e->chain_capture != 0) {  // remember the node this launch became
+        cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
+        const cudaGraphNode_t *deps = nullptr;
+        size_t n_deps = 0;
+        if (cudaStreamGetCaptureInfo(stream, &cst, nullptr, nullptr, &deps, &n_deps) == cudaSuccess && n_deps == 1 && deps) e->chain_node = deps[0];
+        else cudaGetLastError();
+    }
     e->launches++;
     e->chained_launches += P.chain_wait ? 1 : 0;
     return QS_OK;

@@ -127,3 +127,38 @@ def test_two_envs_per_thread_kernel_equals_one_env_kernel(ga, pic, tracks, monke
     np.testing.assert_array_equal(da, db)
     assert sta["dones"] > 0 and {k: v for k, v in sta.items() if k != "reward_sum"} == {k: v for k, v in stb.items() if k != "reward_sum"}
     assert abs(sta["reward_sum"] - stb["reward_sum"]) <= 1e-6 * max(1.0, abs(stb["reward_sum"]))  # other partition of the float sums
+
+
+def test_a_foreign_kernel_between_two_captured_steps_breaks_the_chain(tracks, monkeypatch):
+    """Chaining skips the grid-wide wait, so it is only allowed when the step depends on NOTHING but the previous
+    chained step: any other node captured in between (here the kernel that produces the next actions) is waited for."""
+    import torch
+    monkeypatch.setenv("QS_CHAIN", "1")
+    n = 8192
+    env = make_env("e2e", n, tracks, reset_rng="device", seed=1)
+    env.reset_tensor()
+    a = torch.zeros((n, 4), device="cuda")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        env.step_tensor(a)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        env.step_tensor(a)
+        env.step_tensor(a)          # chained: depends on the previous step only
+        a.add_(0.125)               # a foreign kernel writes the actions
+        env.step_tensor(a)          # not chained
+        env.step_tensor(a)          # chained again
+    assert env.chained_launch_count == 2
+    g.replay()
+    torch.cuda.synchronize()
+    ref = make_env("e2e", n, tracks, reset_rng="device", seed=1)
+    ref.reset_tensor()
+    b = torch.zeros((n, 4), device="cuda")
+    for k in range(5):
+        if k == 3:
+            b.add_(0.125)
+        ref.step_tensor(b)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(env.world_states, ref.world_states)
