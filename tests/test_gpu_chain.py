@@ -162,3 +162,28 @@ def test_a_foreign_kernel_between_two_captured_steps_breaks_the_chain(tracks, mo
         ref.step_tensor(b)
     torch.cuda.synchronize()
     np.testing.assert_array_equal(env.world_states, ref.world_states)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_step_graph_helper_equals_step_by_step(variant, tracks):
+    """env.step_graph(actions (T,N,4)): one chained CUDA graph; every step's outputs equal T step_tensor calls."""
+    import torch
+    n, T = 50_000, 9
+    gen = torch.Generator(device="cuda").manual_seed(8)
+    acts = torch.rand((T, n, 4), device="cuda", generator=gen) * 2 - 1
+    a = make_env(variant, n, tracks, reset_rng="device", seed=2)
+    b = make_env(variant, n, tracks, reset_rng="device", seed=2)
+    for env in (a, b):
+        env.max_steps = 4
+        env.reset_tensor()
+    graph, out = a.step_graph(acts)
+    assert a.chained_launch_count == T - 1
+    for rep in range(2):
+        graph.replay()
+        torch.cuda.synchronize()
+        for t in range(T):
+            o, r, d, f = b.step_tensor(acts[t])
+            assert torch.equal(out["obs"][t], o) and torch.equal(out["rewards"][t], r), (rep, t)
+            assert torch.equal(out["dones"][t], d) and torch.equal(out["flags"][t], f), (rep, t)
+    np.testing.assert_array_equal(a.world_states, b.world_states)
+    np.testing.assert_array_equal(a.current_obs_tensor().cpu().numpy(), b.current_obs_tensor().cpu().numpy())
