@@ -91,6 +91,30 @@ __device__ __forceinline__ void mask_pack_store(const uint32_t *v, unsigned char
     }
 }
 
+// The same masking with the result kept in registers (w: kSlabs x 4 words): the stores follow later, once the
+// weight-gradient GEMM that still reads H through the async proxy has completed (mask_store_packed).
+template <int kSlabs>
+__device__ __forceinline__ void mask_pack_regs(const uint32_t *v, const unsigned char *slab0_row, bool last_zero, uint32_t *w) {
+#pragma unroll
+    for (int q = 0; q < kSlabs; ++q) {
+        const uint4 h = *reinterpret_cast<const uint4 *>(slab0_row + q * kSlab);
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float lo = (hw[k] & 0x0000FFFFu) ? __uint_as_float(v[q * 8 + 2 * k]) : 0.0f;
+            const float hi = (hw[k] & 0xFFFF0000u) ? __uint_as_float(v[q * 8 + 2 * k + 1]) : 0.0f;
+            w[q * 4 + k] = pack_bf16(lo, hi);
+        }
+        if (last_zero && q == kSlabs - 1) w[q * 4 + 3] &= 0x0000FFFFu;
+    }
+}
+template <int kSlabs>
+__device__ __forceinline__ void mask_store_packed(const uint32_t *w, unsigned char *slab0_row) {
+#pragma unroll
+    for (int q = 0; q < kSlabs; ++q)
+        *reinterpret_cast<uint4 *>(slab0_row + q * kSlab) = make_uint4(w[q * 4], w[q * 4 + 1], w[q * 4 + 2], w[q * 4 + 3]);
+}
+
 // dynamic shared memory: [barriers 128 B][weights][X: k1/8 slabs][H1][H2][H3][dOUT: 2 slabs][reduction scratch 64 floats]
 __host__ __device__ constexpr size_t train_smem_bytes(int k1) {
     return 128 + policy_weight_bytes(k1, 3) + (size_t)(k1 / 8) * kSlab + 3 * (size_t)(kPolHidden / 8) * kSlab + 2 * kSlab + 256;
@@ -104,6 +128,7 @@ __global__ void __launch_bounds__(kPolRows, 1) ppo_grad_kernel(const __grid_cons
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar_w = reinterpret_cast<uint64_t *>(smem_raw);
     uint64_t *bar_mma = bar_w + 1;
+    uint64_t *bar_dw = bar_w + 2;  // completion of a stage's weight-gradient GEMM (committed after, and apart from, its dH GEMM)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + 64);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int net = blockIdx.x & 1;                       // 0 = policy network, 1 = value network
@@ -117,6 +142,7 @@ __global__ void __launch_bounds__(kPolRows, 1) ppo_grad_kernel(const __grid_cons
     if (tid == 0) {
         mbar_init(bar_w, 1);
         mbar_init(bar_mma, 1);
+        mbar_init(bar_dw, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(bar_w, P.weight_bytes);
         bulk_load(s_w, net == 0 ? P.w_pi : P.w_vf, P.weight_bytes, bar_w);
@@ -165,6 +191,25 @@ __global__ void __launch_bounds__(kPolRows, 1) ppo_grad_kernel(const __grid_cons
             tc_fence_after();
             issue();
             umma_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, phase);
+        phase ^= 1u;
+        tc_fence_after();
+    };
+    // A backward stage issues TWO groups of MMAs: the dH GEMM the epilogue waits for (bar_mma) and the weight-gradient GEMM,
+    // which nobody reads before the end of the launch -- it only has to be finished before the epilogue overwrites its
+    // operand H with dZ (bar_dw).  The epilogue's TMEM read-out and masking run while that GEMM is still in the tensor pipe.
+    uint32_t phase_dw = 0;
+    auto stage_sync_issue2 = [&](auto &&issue_dh, auto &&issue_dw) {
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_dh();
+            umma_commit(bar_mma);
+            issue_dw();
+            umma_commit(bar_dw);
         }
         mbar_wait(bar_mma, phase);
         phase ^= 1u;
@@ -313,37 +358,35 @@ __global__ void __launch_bounds__(kPolRows, 1) ppo_grad_kernel(const __grid_cons
         // same operands, then masks dH with [H > 0] in place over H (all readers of H have completed by then).
         const bool acc = !first_tile;
         // stage B3: dH3 = dOUT . W4 ; dW4^T += H3^T . dOUT
-        stage_sync_issue([&] {
+        stage_sync_issue2([&] {
             const uint32_t idesc = umma_idesc_bf16_ex(kPolRows, kPolHidden, false, true);
             umma_bf16(tmem + kTmAcc, umma_desc(do_smem, kSlab, 128), umma_desc(w4_smem, 128, kPolOut * 16), idesc, false);
-            mma_dw(tmem + kTmDW4, h3_smem, do_smem, kPolOut, acc);
-        });
+        }, [&] { mma_dw(tmem + kTmDW4, h3_smem, do_smem, kPolOut, acc); });
         auto mask_epilogue = [&](unsigned char *h) {
-            uint32_t v0[32], v1[32];
+            uint32_t v0[32], v1[32], w[64];
             unsigned char *dst = h + tid * 16;
             tmem_ld32(t_lane + kTmAcc, v0);
             tmem_ld32(t_lane + kTmAcc + 32u, v1);
             tmem_ld_wait();
-            mask_pack_store<4>(v0, dst, false);
-            mask_pack_store<4>(v1, dst + 4 * kSlab, false);
+            mask_pack_regs<4>(v0, dst, false, w);
+            mask_pack_regs<4>(v1, dst + 4 * kSlab, false, w + 16);
             tmem_ld32(t_lane + kTmAcc + 64u, v0);
             tmem_ld32(t_lane + kTmAcc + 96u, v1);
             tmem_ld_wait();
-            mask_pack_store<4>(v0, dst + 8 * kSlab, false);
-            mask_pack_store<4>(v1, dst + 12 * kSlab, true);   // the constant-1 unit takes no gradient
+            mask_pack_regs<4>(v0, dst + 8 * kSlab, false, w + 32);
+            mask_pack_regs<4>(v1, dst + 12 * kSlab, true, w + 48);   // the constant-1 unit takes no gradient
+            mbar_wait(bar_dw, phase_dw);                              // the weight-gradient GEMM has finished reading H
+            phase_dw ^= 1u;
+            mask_store_packed<16>(w, dst);
         };
         mask_epilogue(s_h3);                                   // H3 <- dZ3
         // stage B2: dH2 = dZ3 . W3 ; dW3 += dZ3^T . H2
-        stage_sync_issue([&] {
-            mma_bwd(tmem + kTmAcc, h3_smem, w3_smem, kPolHidden, kSlab);
-            mma_dw(tmem + kTmDW3, h3_smem, h2_smem, kPolHidden, acc);
-        });
+        stage_sync_issue2([&] { mma_bwd(tmem + kTmAcc, h3_smem, w3_smem, kPolHidden, kSlab); },
+                          [&] { mma_dw(tmem + kTmDW3, h3_smem, h2_smem, kPolHidden, acc); });
         mask_epilogue(s_h2);                                   // H2 <- dZ2
         // stage B1: dH1 = dZ2 . W2 ; dW2 += dZ2^T . H1
-        stage_sync_issue([&] {
-            mma_bwd(tmem + kTmAcc, h2_smem, w2_smem, kPolHidden, kSlab);
-            mma_dw(tmem + kTmDW2, h2_smem, h1_smem, kPolHidden, acc);
-        });
+        stage_sync_issue2([&] { mma_bwd(tmem + kTmAcc, h2_smem, w2_smem, kPolHidden, kSlab); },
+                          [&] { mma_dw(tmem + kTmDW2, h2_smem, h1_smem, kPolHidden, acc); });
         mask_epilogue(s_h1);                                   // H1 <- dZ1
         // stage B0: dW1 += dZ1^T . X  (no gradient flows to the observations).  Waited for here because the next tile
         // overwrites X and H1 while this GEMM would still be reading them.
