@@ -878,7 +878,7 @@ constexpr int kBarBytes = 256;  // mbarriers live in the first 256 bytes of dyna
 #endif
 template <int V> struct StepCta {
     enum : int { WARPS = (V == kE2E ? QS_E2E_WARPS : 4), THREADS = WARPS * 32,
-                 MIN_CTAS = (V == kE2E ? (QS_E2E_WARPS == 7 ? 3 : QS_E2E_WARPS == 4 ? 5 : 1) : 8) };
+                 MIN_CTAS = (V == kE2E ? (QS_E2E_WARPS == 7 ? 3 : QS_E2E_WARPS == 4 ? 5 : QS_E2E_WARPS == 2 ? 10 : 1) : 8) };
 };
 __host__ __device__ constexpr int step_warps(int variant) { return variant == kE2E ? (int)StepCta<kE2E>::WARPS : (int)StepCta<kINDI>::WARPS; }
 

@@ -238,9 +238,9 @@ class PPO:
         if use_sde or clip_range_vf is not None:
             raise NotImplementedError("use_sde / clip_range_vf are not used by the reference and not implemented")
         if rollout not in ("auto", "device", "host") or bootstrap not in (None, "none", "sb3_a8") or \
-                update not in ("auto", "torch", "fused") or evaluate not in ("auto", "torch", "device"):
+                update not in ("auto", "torch", "fused") or evaluate not in ("auto", "torch", "device", "mixed"):
             raise ValueError("rollout in {auto, device, host}; bootstrap in {None, 'none', 'sb3_a8'}; update in {auto, torch, fused}; "
-                             "evaluate in {auto, torch, device}")
+                             "evaluate in {auto, torch, device, mixed}")
         self.env = env
         self.venv = getattr(env, "venv", env)  # VecMonitor(env) -> env
         self.learning_rate, self.n_steps, self.batch_size, self.n_epochs = float(learning_rate), int(n_steps), int(batch_size), int(n_epochs)
@@ -299,12 +299,18 @@ class PPO:
         # the E2E env the one 130 s run with it plateaued at ep_rew_mean 115 - 137 instead of 145 - 160 (profiles/r2/ppo/):
         # opt-in, for when the collect phase matters more than the last gates per episode.
         fits_vf = act is not None and vf == pi and fits
+        # "mixed": values in float32 / TF32 (torch), old log-probs from the tcgen05 actor -- the BF16 operands the sampling
+        # actor and the fused trainer use, so the first epoch's PPO ratio is exactly 1 -- which drops the torch policy
+        # forward over the buffer without touching the critic's precision.
         if evaluate == "device" and not (fits_vf and self.rollout == "device"):
             raise ValueError("evaluate='device' needs rollout='device' and pi / vf networks of the same supported shape")
-        self.evaluate = "device" if evaluate == "device" else "torch"
+        if evaluate == "mixed" and not (act is not None and fits and self.rollout == "device"):
+            raise ValueError("evaluate='mixed' needs rollout='device' and a policy network of the supported shape")
+        self.evaluate = evaluate if evaluate in ("device", "mixed") else "torch"
         self.eval_actor = self.critic = None
-        if self.evaluate == "device":
+        if self.evaluate in ("device", "mixed"):
             self.eval_actor = MlpPolicy(*self._pi_arrays(), device=self.device, activation=act, obs_limit=self.obs_limit)
+        if self.evaluate == "device":
             self.critic = MlpPolicy(*self._vf_arrays(), device=self.device, activation=act, obs_limit=self.obs_limit)
 
     # convenient aliases used by the tests / tools of this repository
@@ -333,6 +339,7 @@ class PPO:
             self.actor.set_weights(w, b, std=self.policy.log_std.detach().exp().cpu().numpy())
             if self.eval_actor is not None:
                 self.eval_actor.set_weights(w, b)
+            if self.critic is not None:
                 self.critic.set_weights(*self._vf_arrays())
 
     def _sane(self, obs):
@@ -395,6 +402,14 @@ class PPO:
                     ok &= torch.isfinite(ra).all(-1) & (ra.abs().amax(-1) <= self._ACT_LIMIT)
                     ok &= torch.isfinite(b["rewards"][t0:e])
                     b["weights"][t0:e] = ok.float()
+            if self.evaluate == "mixed":  # the policy mean from the tcgen05 forward kernel (one launch over the buffer)
+                rows = T * n
+                if getattr(self, "_eval_scratch", None) is None or self._eval_scratch[0].shape[0] < rows:
+                    self._eval_scratch = (torch.empty((rows, 4), device=self.device), torch.empty((rows, 4), device=self.device))
+                out4, mean4 = self._eval_scratch
+                self.eval_actor.forward(b["obs"][:T].reshape(rows, d), deterministic=True, out=out4[:rows], mean_out=mean4[:rows])
+                b["log_probs"].copy_(self.policy.log_prob(mean4[:rows], self._sane_act(b["raw_actions"].reshape(rows, 4))).reshape(T, n))
+                return
             for t0 in range(0, T, chunk):
                 t1 = min(T, t0 + chunk)
                 b["log_probs"][t0:t1] = self._log_prob(b["obs"][t0:t1].reshape(-1, d),

@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--amp", action="store_true", help="BF16 autocast of the update's GEMMs")
     ap.add_argument("--bootstrap", default="none", choices=["none", "sb3_a8"])
     ap.add_argument("--update", default="auto", choices=["auto", "torch", "fused"])
+    ap.add_argument("--evaluate", default="auto", choices=["auto", "torch", "device", "mixed"],
+                    help="values / old log-probs over the rollout buffer (see PPO.__init__)")
     ap.add_argument("--save", default=None, help="checkpoint path written at the end (model.save)")
     a = ap.parse_args()
     import optimal_quad_control_rl_b200 as Q
@@ -35,7 +37,7 @@ def main():
     import torch
     pk = dict(activation_fn=torch.nn.ReLU, net_arch=[dict(pi=[120, 120, 120], vf=[120, 120, 120])], log_std_init=0)
     ppo = Q.PPO("MlpPolicy", Q.VecMonitor(env), policy_kwargs=pk, n_steps=a.n_steps, batch_size=a.batch_size,
-                n_epochs=a.n_epochs, gamma=0.999, learning_rate=a.lr, amp=a.amp, bootstrap=a.bootstrap, update=a.update)
+                n_epochs=a.n_epochs, gamma=0.999, learning_rate=a.lr, amp=a.amp, bootstrap=a.bootstrap, update=a.update, evaluate=a.evaluate)
     ppo.learn(wall_clock_s=None if a.iterations else a.seconds, iterations=a.iterations,
               log=lambda r: print(json.dumps(r), flush=True))
     if a.save:
