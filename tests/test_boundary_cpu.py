@@ -147,3 +147,38 @@ def test_obs_all_gather_world_size_2_gloo(tmp_path):
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0, out
         assert f"ok {r}" in out
+
+
+def test_shipped_sass_uses_the_blackwell_paths_the_design_claims():
+    """DESIGN.md section 3 claims per kernel: TMA bulk copies (UBLKCP) + packed FP32 FMAs (FFMA2) in the step kernels,
+    tcgen05.mma / TMEM loads (UTCHMMA / LDTM) in the policy, rollout and PPO-update kernels, tcgen05.st (STTM) in the
+    TMEM-resident policy variant.  Read from the SASS of the library that ships (no GPU needed)."""
+    out = subprocess.run(["cuobjdump", "-sass", os.path.join(PKG, "libquadsim.so")], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    import collections
+    hist, fn = collections.defaultdict(collections.Counter), None
+    for line in out.stdout.splitlines():
+        if "Function :" in line:
+            fn = line.split("Function :")[1].strip()
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P[0-9T]+\s+)?([A-Z0-9_]+)", line)
+        if fn and m:
+            hist[fn][m.group(1)] += 1
+
+    def kernels(sub):
+        ks = [k for k in hist if sub in k]
+        assert ks, sub
+        return ks
+
+    for k in kernels("11step_kernelILi0E"):  # E2E: residual nets as 336 packed FMAs, bulk copies in and out
+        assert hist[k]["FFMA2"] >= 336 and hist[k]["UBLKCP"] >= 8, (k, hist[k]["FFMA2"], hist[k]["UBLKCP"])
+    for k in kernels("11step_kernelILi1E"):  # INDI: no nets
+        assert hist[k]["UBLKCP"] >= 8 and hist[k]["FFMA2"] == 0, k
+    for sub in ("13policy_kernelE", "14rollout_kernelILi0E", "14rollout_kernelILi1E", "15ppo_grad_kernelE"):
+        for k in kernels(sub):
+            assert hist[k]["UTCHMMA"] >= 7 and hist[k]["LDTM"] >= 3 and hist[k]["UTCBAR"] >= 1, (k, dict(hist[k]))
+    ts, = kernels("16policy_kernel_tsE")
+    assert hist[ts]["STTM"] >= 1 and hist[ts]["UTCHMMA"] >= 7
+    # nothing falls back to the legacy tensor-core path
+    assert not any(c["HMMA"] or c["HGMMA"] for c in hist.values())
