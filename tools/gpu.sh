@@ -11,6 +11,7 @@
 #   numpy              the NumPy-facing env.step (what SB3 calls) at N = 100 .. 2^20
 #   ppo <seconds> [train_ppo.py args]   BASELINE config 5: PPO to the plateau, log + summary
 #   multi <ngpus>      multi-GPU test + bench.py under torchrun (ours, reference arm)
+#   sanitize [secs]    compute-sanitizer: memcheck over the GPU tests, racecheck + synccheck over smoke()
 # Experimental libraries are built HERE (CPU box) first:   bash tools/gpu.sh build-variants name=-DFLAG ...
 cmd=${1:-check}; tag=${2:-r}; shift 2 2>/dev/null
 mkdir -p gpurun_out
@@ -110,6 +111,20 @@ multi)
   timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 400 --warmup 50 \
       > gpurun_out/${tag}_bench_${n}gpu.json 2> gpurun_out/${tag}_bench_${n}gpu.err; line "${n}gpu" < gpurun_out/${tag}_bench_${n}gpu.json; tail -3 gpurun_out/${tag}_bench_${n}gpu.err
   timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $n --impl reference --steps 5 --warmup 1 2>/dev/null | tail -c 600
+  ;;
+sanitize)
+  secs=${1:-110}
+  for grp in "step:tests/test_gpu_parity.py tests/test_gpu_chain.py tests/test_gpu_packed_obs.py" \
+             "tensor:tests/test_gpu_policy.py tests/test_gpu_rollout_fused.py" "train:tests/test_gpu_train.py tests/test_gpu_ppo.py"; do
+    name=${grp%%:*}; files=${grp#*:}
+    timeout $secs compute-sanitizer --tool memcheck --print-limit 30 --error-exitcode 7 \
+        python -m pytest $files -m gpu -q -p no:cacheprovider --timeout 120 > gpurun_out/${tag}_memcheck_$name.log 2>&1
+    echo "memcheck $name rc=$?"; grep -E "ERROR SUMMARY|passed|failed|Invalid|out of bounds|misaligned|Timeout" gpurun_out/${tag}_memcheck_$name.log | sort | uniq -c | head -12
+  done
+  for tool in racecheck synccheck; do
+    timeout 80 compute-sanitizer --tool $tool --print-limit 30 --error-exitcode 7 python __graft_entry__.py smoke > gpurun_out/${tag}_$tool.log 2>&1
+    echo "$tool rc=$?"; grep -E "SUMMARY|smoke|hazard|Barrier error" gpurun_out/${tag}_$tool.log | sort | uniq -c | head -12
+  done
   ;;
 *) echo "unknown command $cmd"; exit 2;;
 esac
