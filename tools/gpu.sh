@@ -122,7 +122,7 @@ sanitize)
     echo "memcheck $name rc=$?"; grep -E "ERROR SUMMARY|passed|failed|Invalid|out of bounds|misaligned|Timeout" gpurun_out/${tag}_memcheck_$name.log | sort | uniq -c | head -12
   done
   for tool in racecheck synccheck; do
-    timeout 80 compute-sanitizer --tool $tool --print-limit 30 --error-exitcode 7 python __graft_entry__.py smoke > gpurun_out/${tag}_$tool.log 2>&1
+    timeout 110 compute-sanitizer --tool $tool --print-limit 30 --error-exitcode 7 --launch-timeout 100 python -c 'import __graft_entry__ as g; g.smoke()' > gpurun_out/${tag}_$tool.log 2>&1
     echo "$tool rc=$?"; grep -E "SUMMARY|smoke|hazard|Barrier error" gpurun_out/${tag}_$tool.log | sort | uniq -c | head -12
   done
   ;;
