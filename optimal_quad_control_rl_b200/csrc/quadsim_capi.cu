@@ -55,6 +55,7 @@ struct qs_env {
     uint64_t launches = 0, chained_launches = 0;
     cudaStream_t copy_a = nullptr, copy_b = nullptr;  // host-buffer pipeline: upload+kernel / download
     cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr;
+    int host_first_div = 4;  // first chunk = 1/div of an equal share (qs_step_host_ex): 2^20 envs 2092 -> 2037 us per step, 8: 2073, 2: 2080
     int host_chunks = 4;   // measured on B200 + PCIe Gen5: 1 -> 4.67e8, 4 -> 5.13e8 env-steps/s at N = 2^20
     int stages = 2, step_grid = 0;  // pipeline depth and persistent grid of the step kernel
     int stats_slots = 0;            // statistics / chain-ticket slots: one per CTA of the larger of the two step grids
@@ -681,6 +682,7 @@ static int ensure_io(qs_env *e) {
     QS_CUDA(e, cudaEventCreateWithFlags(&e->ev_k, cudaEventDisableTiming));
     QS_CUDA(e, cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
     if (const char *cv = getenv("QS_HOST_CHUNKS")) { int v = atoi(cv); if (v >= 1 && v <= 64) e->host_chunks = v; }
+    if (const char *cv = getenv("QS_HOST_FIRST_DIV")) { int v = atoi(cv); if (v >= 1 && v <= 64) e->host_first_div = v; }
     {   // staging threads of qs_step_host_ex: a few are enough to outrun PCIe; QS_HOST_THREADS overrides
         const unsigned hc = std::thread::hardware_concurrency();
         e->host_threads = hc >= 16 ? 6 : (hc >= 4 ? (int)hc / 2 : 1);
@@ -722,27 +724,35 @@ int qs_step_host_ex(qs_env *e, const void *act, int act_dtype, float *obs, float
     const int chunks = stage ? 2 * e->host_chunks : e->host_chunks;
     long long per = (tiles + chunks - 1) / chunks;
     if (per < 256) per = tiles < 256 ? tiles : 256;  // >= 32768 envs per chunk: below that the copies are latency-bound
+    // The download is the long pole (101 B per env against 16 B up): nothing comes back before the first chunk's
+    // upload + kernel are through, so the first chunk is a fraction of the others (QS_HOST_FIRST_DIV, 1 = equal chunks)
+    long long first = per;
+    if (e->host_first_div > 1 && chunks > 1 && per / e->host_first_div >= 256) {
+        first = per / e->host_first_div;
+        per = (tiles - first + chunks - 2) / (chunks - 1);
+    }
     const bool want_obs = obs && mode != QS_MODE_PAUSE;
     if (stage && !e->act_stage) QS_CUDA(e, cudaHostAlloc((void **)&e->act_stage, (size_t)e->n * 16, cudaHostAllocDefault));
     QS_CUDA(e, cudaEventRecord(e->ev_in, e->stream));
     QS_CUDA(e, cudaStreamWaitEvent(e->copy_a, e->ev_in, 0));
     QS_CUDA(e, cudaStreamWaitEvent(e->copy_b, e->ev_in, 0));
-    for (long long t0 = 0; t0 < tiles; t0 += per) {
-        const long long t1 = t0 + per < tiles ? t0 + per : tiles;
-        const size_t first = (size_t)t0 * qs::kBlock;
-        const size_t cnt = (size_t)((t1 * qs::kBlock < e->n ? t1 * qs::kBlock : e->n)) - first;
-        const float *src = (const float *)act + first * 4;
+    for (long long t0 = 0, t1 = 0; t0 < tiles; t0 = t1) {
+        t1 = t0 + (t0 == 0 ? first : per);
+        if (t1 > tiles) t1 = tiles;
+        const size_t first_env = (size_t)t0 * qs::kBlock;
+        const size_t cnt = (size_t)((t1 * qs::kBlock < e->n ? t1 * qs::kBlock : e->n)) - first_env;
+        const float *src = (const float *)act + first_env * 4;
         if (stage) {  // the previous step's uploads completed before that call returned: the staging buffer is free
             // a few host threads per chunk: one core copies ~8 GB/s, the 16 MB of a 2^20-env action array would cost
             // as much as the whole PCIe transfer of the results
-            float *dst = e->act_stage + first * 4;
+            float *dst = e->act_stage + first_env * 4;
             const long long pieces = (long long)((cnt * 16 + 262143) / 262144);  // 256 KB per piece
             const int threads = (int)(pieces < e->host_threads ? pieces : e->host_threads);
 #pragma omp parallel for num_threads(threads) schedule(static) if (threads > 1)
             for (long long p = 0; p < pieces; ++p) {
                 const size_t a = (size_t)p * 16384, b = a + 16384 < cnt ? a + 16384 : cnt;  // envs [a, b) of this chunk
                 if (act_dtype == QS_F64) {
-                    const double *s64 = (const double *)act + first * 4;
+                    const double *s64 = (const double *)act + first_env * 4;
                     for (size_t i = a * 4; i < b * 4; ++i) dst[i] = (float)s64[i];
                 } else {
                     memcpy(dst + a * 4, src + a * 4, (b - a) * 16);
@@ -750,16 +760,16 @@ int qs_step_host_ex(qs_env *e, const void *act, int act_dtype, float *obs, float
             }
             src = dst;
         }
-        QS_CUDA(e, cudaMemcpyAsync(e->h_act + first * 4, src, cnt * 16, cudaMemcpyHostToDevice, e->copy_a));
+        QS_CUDA(e, cudaMemcpyAsync(e->h_act + first_env * 4, src, cnt * 16, cudaMemcpyHostToDevice, e->copy_a));
         if (int r = launch_step(e, t0, t1, t1 == tiles, e->copy_a, false)) return r;
         QS_CUDA(e, cudaEventRecord(e->ev_k, e->copy_a));
         QS_CUDA(e, cudaStreamWaitEvent(e->copy_b, e->ev_k, 0));
         if (want_obs)
-            QS_CUDA(e, cudaMemcpyAsync(obs + first * e->obs_len, e->h_obs + first * e->obs_len, cnt * e->obs_len * 4,
+            QS_CUDA(e, cudaMemcpyAsync(obs + first_env * e->obs_len, e->h_obs + first_env * e->obs_len, cnt * e->obs_len * 4,
                                        cudaMemcpyDeviceToHost, e->copy_b));
-        QS_CUDA(e, cudaMemcpyAsync(rew + first, e->h_rew + first, cnt * 4, cudaMemcpyDeviceToHost, e->copy_b));
-        QS_CUDA(e, cudaMemcpyAsync(done + first, e->h_done + first, cnt, cudaMemcpyDeviceToHost, e->copy_b));
-        if (flags) QS_CUDA(e, cudaMemcpyAsync(flags + first, e->h_flags + first, cnt, cudaMemcpyDeviceToHost, e->copy_b));
+        QS_CUDA(e, cudaMemcpyAsync(rew + first_env, e->h_rew + first_env, cnt * 4, cudaMemcpyDeviceToHost, e->copy_b));
+        QS_CUDA(e, cudaMemcpyAsync(done + first_env, e->h_done + first_env, cnt, cudaMemcpyDeviceToHost, e->copy_b));
+        if (flags) QS_CUDA(e, cudaMemcpyAsync(flags + first_env, e->h_flags + first_env, cnt, cudaMemcpyDeviceToHost, e->copy_b));
     }
     if (info) {  // the `infos` scan (`:589-594`) as one tiny kernel over the flag bytes, behind the last chunk's step
         if (!e->info_dev) {

@@ -407,12 +407,14 @@ def test_few_resets_per_warp_use_cooperative_draw_and_match_per_lane_draw(varian
     np.testing.assert_array_equal(outs[0][0][sel], outs[1][0][sel])
 
 
-@pytest.mark.parametrize("n", [5000, 100003])
-def test_c_abi_host_step_matches_device_step(n, tracks):
-    """qs_step_host (HOST buffers in/out; chunk-pipelined above 32768 envs) == qs_step on device buffers,
-    bit for bit, fused resets included."""
+@pytest.mark.parametrize("n,first_div", [(5000, None), (100003, None), (600001, "1"), (600001, "4"), (600001, "2")])
+def test_c_abi_host_step_matches_device_step(n, first_div, tracks, monkeypatch):
+    """qs_step_host (HOST buffers in/out; chunk-pipelined above 32768 envs, equal chunks or a shorter first one) ==
+    qs_step on device buffers, bit for bit, fused resets included."""
     import ctypes as C
     import optimal_quad_control_rl_b200._lib as L
+    if first_div is not None:  # read by the library at an env's first host-buffer call
+        monkeypatch.setenv("QS_HOST_FIRST_DIV", first_div)
     e1 = make_env("e2e", n, tracks, reset_rng="device", seed=3)
     e2 = make_env("e2e", n, tracks, reset_rng="device", seed=3)
     o1 = e1.reset()

@@ -12,6 +12,7 @@
 #   ppo <seconds> [train_ppo.py args]   BASELINE config 5: PPO to the plateau, log + summary
 #   multi <ngpus>      multi-GPU test + bench.py under torchrun (ours, reference arm)
 #   sanitize [secs]    compute-sanitizer: memcheck over the GPU tests, racecheck + synccheck over smoke()
+#   hostpipe           qs_step_host: host-path tests + sweep of (chunks, first-chunk divisor) on the e2e number
 # Experimental libraries are built HERE (CPU box) first:   bash tools/gpu.sh build-variants name=-DFLAG ...
 cmd=${1:-check}; tag=${2:-r}; shift 2 2>/dev/null
 mkdir -p gpurun_out
@@ -111,6 +112,15 @@ multi)
   timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 400 --warmup 50 \
       > gpurun_out/${tag}_bench_${n}gpu.json 2> gpurun_out/${tag}_bench_${n}gpu.err; line "${n}gpu" < gpurun_out/${tag}_bench_${n}gpu.json; tail -3 gpurun_out/${tag}_bench_${n}gpu.err
   timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $n --impl reference --steps 5 --warmup 1 2>/dev/null | tail -c 600
+  ;;
+hostpipe)
+  timeout 120 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "host_step or numpy_step" 2>&1 | tail -3
+  for cd in "4 1" "4 4" "4 8" "5 4" "6 4" "4 2" "3 4" "4 1" "4 4"; do
+    set -- $cd
+    QS_HOST_CHUNKS=$1 QS_HOST_FIRST_DIV=$2 timeout 60 python bench.py --steps 200 --warmup 20 --no-cpu-baseline --no-configs --e2e-steps 80 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('chunks $1 first_div $2 e2e %.4g  us/step(host) %.1f' % (d['e2e']['value'], 1048576/d['e2e']['value']*1e6))"
+  done | tee gpurun_out/${tag}_host_first_div_sweep.log
   ;;
 sanitize)
   secs=${1:-110}
