@@ -539,10 +539,17 @@ def config4(torch, dist, Q, L, dev, rank, world, local, steps, barrier, peak, to
                "per_gpu_roofline_frac": count * bpe / (ms * 1e-3) / 1e9 / peak,
                "nvlink_algorithmic_rx_bytes_per_gpu_per_step": 0 if gather is None else
                (total - count) * (16 * ((env.state_len + 7) // 8) if mode == "p2p_bf16" else env.state_len * 4)}
-        if nv0 and nv1:
+        if gather is not None:  # what the gather must deliver per GPU, over the measured step time
+            rec["nvlink_algorithmic_rx_GBps_per_gpu"] = rec["nvlink_algorithmic_rx_bytes_per_gpu_per_step"] / (ms * 1e-3) / 1e9
+        if nv0 and nv1 and (gather is None or nv1[1] > nv0[1]):
             rec["nvlink_measured_bytes_per_step_rank0"] = {"tx": (nv1[0] - nv0[0]) * 1024 / steps, "rx": (nv1[1] - nv0[1]) * 1024 / steps}
             if gather is not None:
                 rec["nvlink_rx_GBps_rank0"] = (nv1[1] - nv0[1]) * 1024 / steps / (ms * 1e-3) / 1e9
+        elif gather is not None:  # counters that stand still while a verified gather runs are not a measurement of zero
+            rec["nvlink_measured_bytes_per_step_rank0"] = None
+            rec["nvlink_counters"] = ("unavailable" if not (nv0 and nv1) else
+                                      "NVML / nvidia-smi NVLink data counters did not advance on this box during a gather "
+                                      "whose result the selfcheck verifies (not exposed to the container)")
         out.append(rec)
         env.close()
         del gather
