@@ -163,7 +163,10 @@ int qs_apply_reset(qs_env *env, int64_t count, const int32_t *env_index, const f
 
 /* ---- host-buffer convenience: what a NumPy-facing VecEnv calls --------------------------------------------- */
 /* One full step with HOST buffers: copies actions in, steps, copies obs/rew/done(/flags) out, synchronises.
- * Buffers from qs_host_alloc are pinned and make the copies asynchronous DMA. */
+ * Buffers from qs_host_alloc are pinned and make the copies asynchronous DMA.  Above 32768 envs the call is pipelined
+ * over chunks of envs (upload + kernel of chunk c+1 under the download of chunk c; same bits as one qs_step): four chunks,
+ * the first a quarter of an equal share so that the download -- 101 of the 117 bytes per env -- starts early.
+ * QS_HOST_CHUNKS / QS_HOST_FIRST_DIV in the environment override both (read at an env's first host-buffer call). */
 int qs_step_host(qs_env *env, const float *actions_host, float *obs_host, float *rew_host, uint8_t *done_host,
                  uint8_t *flags_host, int mode, int reset_source);
 /* The same step for the arrays a NumPy caller really has: `actions_host` is (num_envs,4) float32 or float64
